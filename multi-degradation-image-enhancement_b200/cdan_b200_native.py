@@ -1,0 +1,237 @@
+"""ctypes binding of libcdan_b200.so (the C ABI declared in include/cdan_b200.h).
+
+PyTorch is used only for device memory and streams: tensors are passed as raw ``data_ptr()`` values and the
+current CUDA stream handle.  If the shared library is missing this module raises — there is no PyTorch / CPU
+fallback behind it.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Iterable, Optional, Tuple
+
+import torch
+
+DTYPE_F32 = 0
+DTYPE_BF16 = 1
+_DTYPE_NAMES = {"fp32": DTYPE_F32, "float32": DTYPE_F32, "f32": DTYPE_F32, "bf16": DTYPE_BF16, "bfloat16": DTYPE_BF16}
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB: Optional[ctypes.CDLL] = None
+
+_c_int, _c_void_p, _c_char_p, _c_float = ctypes.c_int, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_float
+_PROTOTYPES = {
+    "cdan_last_error": (_c_char_p, []),
+    "cdan_version": (_c_char_p, []),
+    "cdan_plan_create": (_c_int, [_c_int, _c_int, ctypes.POINTER(_c_void_p)]),
+    "cdan_plan_destroy": (_c_int, [_c_void_p]),
+    "cdan_plan_load_weights": (_c_int, [_c_void_p, _c_int, ctypes.POINTER(_c_char_p), ctypes.POINTER(_c_void_p),
+                                        ctypes.POINTER(ctypes.c_int64)]),
+    "cdan_plan_set_option": (_c_int, [_c_void_p, _c_char_p, _c_int]),
+    "cdan_workspace_bytes": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, ctypes.POINTER(ctypes.c_size_t)]),
+    "cdan_forward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
+    "cdan_forward_host": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
+    "cdan_stage_read": (_c_int, [_c_void_p, _c_void_p, _c_char_p, _c_void_p, ctypes.POINTER(ctypes.c_int64)]),
+    "cdan_last_launch_count": (_c_int, [_c_void_p]),
+    "cdan_op_conv2d": (_c_int, [_c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p,
+                                _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
+    "cdan_op_cbam": (_c_int, [_c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
+                              _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "cdan_op_upsample_add": (_c_int, [_c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                      _c_void_p]),
+    "cdan_postprocess": (_c_int, [_c_void_p, _c_int, _c_float, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
+    "cdan_psnr_ssim": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
+                                ctypes.POINTER(_c_float)]),
+}
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+
+
+def library_path() -> str:
+    return os.environ.get("CDAN_B200_LIB", os.path.join(_HERE, "csrc", "libcdan_b200.so"))
+
+
+def lib() -> ctypes.CDLL:
+    """Load the shared library once; fail loudly when it is absent."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"cdan_b200: native library not found at {path}. Build it with "
+                f"`bash {os.path.join(_HERE, 'csrc', 'build.sh')}` (nvcc, sm_100a). "
+                "The CUDA kernels are the product: there is no PyTorch or CPU fallback.")
+        handle = ctypes.CDLL(path)
+        for name, (restype, argtypes) in _PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = restype, argtypes
+        _LIB = handle
+    return _LIB
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"cdan_b200::{what} failed: {lib().cdan_last_error().decode(errors='replace')}")
+
+
+def dtype_code(dtype) -> int:
+    if isinstance(dtype, int):
+        return dtype
+    if isinstance(dtype, torch.dtype):
+        return {torch.float32: DTYPE_F32, torch.bfloat16: DTYPE_BF16}[dtype]
+    return _DTYPE_NAMES[str(dtype).lower()]
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _f32(t: torch.Tensor, device: torch.device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class Plan:
+    """One (device, dtype) execution plan: packed weights + workspace inside the native library."""
+
+    def __init__(self, device: torch.device, dtype="bf16"):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("cdan_b200: plans exist only on CUDA devices (no CPU fallback)")
+        self.device = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+        self.dtype = dtype_code(dtype)
+        self._h = ctypes.c_void_p()
+        _check(lib().cdan_plan_create(self.device.index, self.dtype, ctypes.byref(self._h)), "plan_create")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            lib().cdan_plan_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name: str, value: int) -> None:
+        _check(lib().cdan_plan_set_option(self._h, name.encode(), int(value)), "plan_set_option")
+
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        items = [(k, v) for k, v in state_dict.items() if not k.endswith("num_batches_tracked")]
+        keep = [v.detach().to(torch.float32).contiguous() for _, v in items]  # host or device, both accepted
+        n = len(items)
+        keys = (_c_char_p * n)(*[k.encode() for k, _ in items])
+        ptrs = (_c_void_p * n)(*[t.data_ptr() for t in keep])
+        numels = (ctypes.c_int64 * n)(*[t.numel() for t in keep])
+        if any(t.is_cuda for t in keep):
+            torch.cuda.synchronize(self.device)
+        _check(lib().cdan_plan_load_weights(self._h, n, keys, ptrs, numels), "plan_load_weights")
+
+    def workspace_bytes(self, n: int, h: int, w: int) -> int:
+        out = ctypes.c_size_t()
+        _check(lib().cdan_workspace_bytes(self._h, n, h, w, ctypes.byref(out)), "workspace_bytes")
+        return out.value
+
+    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise RuntimeError(f"cdan_b200: expected input [N,3,H,W], got {tuple(x.shape)}")
+        if x.device != self.device:
+            raise RuntimeError(f"cdan_b200: input on {x.device}, plan on {self.device}")
+        x = x.detach().to(torch.float32).contiguous()
+        y = out if out is not None else torch.empty_like(x)
+        n, _, h, w = x.shape
+        with torch.cuda.device(self.device):
+            _check(lib().cdan_forward(self._h, _c_void_p(_stream(self.device)), _ptr(x), _ptr(y), n, h, w), "forward")
+        return y
+
+    def forward_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Host buffers in/out (pinned memory recommended); copies + forward + sync happen in the library."""
+        if x_host.is_cuda or x_host.dtype != torch.float32 or not x_host.is_contiguous():
+            raise RuntimeError("cdan_b200: forward_host needs a contiguous fp32 CPU tensor")
+        y = out_host if out_host is not None else torch.empty_like(x_host)
+        n, _, h, w = x_host.shape
+        _check(lib().cdan_forward_host(self._h, _ptr(x_host), _ptr(y), n, h, w), "forward_host")
+        return y
+
+    def stage(self, name: str) -> torch.Tensor:
+        shape = (ctypes.c_int64 * 4)()
+        s = _c_void_p(_stream(self.device))
+        _check(lib().cdan_stage_read(self._h, s, name.encode(), None, shape), "stage_read")
+        out = torch.empty(tuple(shape), dtype=torch.float32, device=self.device)
+        _check(lib().cdan_stage_read(self._h, s, name.encode(), _ptr(out), shape), "stage_read")
+        return out
+
+    @property
+    def last_launch_count(self) -> int:
+        return lib().cdan_last_launch_count(self._h)
+
+
+# ------------------------------------------------------------------------------------------------ single operators
+def op_conv2d(x, w, bias=None, pre_scale=None, pre_shift=None, relu=False, pool=False, dtype="fp32", impl=0):
+    dev = x.device
+    x, w = _f32(x, dev), _f32(w, dev)
+    bias = None if bias is None else _f32(bias, dev)
+    pre_scale = None if pre_scale is None else _f32(pre_scale, dev)
+    pre_shift = None if pre_shift is None else _f32(pre_shift, dev)
+    n, cin, h, wd = x.shape
+    cout, _, ks, _ = w.shape
+    y = torch.empty((n, cout, h // 2 if pool else h, wd // 2 if pool else wd), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib().cdan_op_conv2d(dtype_code(dtype), impl, _c_void_p(_stream(dev)), _ptr(x), n, cin, h, wd, _ptr(w),
+                                    _ptr(bias), cout, ks, _ptr(pre_scale), _ptr(pre_shift), int(relu), int(pool),
+                                    _ptr(y)), "op_conv2d")
+    return y
+
+
+def op_cbam(x, w1, b1, w2, b2, w7, bn4: Iterable[float], mul=None, dtype="fp32"):
+    dev = x.device
+    x = _f32(x, dev)
+    ws = [_f32(t, dev) for t in (w1, b1, w2, b2, w7)]
+    mul = None if mul is None else _f32(mul, dev)
+    bn = (ctypes.c_float * 4)(*[float(v) for v in bn4])
+    n, c, h, w = x.shape
+    y = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        _check(lib().cdan_op_cbam(dtype_code(dtype), _c_void_p(_stream(dev)), _ptr(x), n, c, h, w, *[_ptr(t) for t in ws],
+                                  ctypes.cast(bn, _c_void_p), _ptr(mul), _ptr(y)), "op_cbam")
+    return y
+
+
+def op_upsample_add(a, skip, up=True, dtype="fp32"):
+    dev = a.device
+    a, skip = _f32(a, dev), _f32(skip, dev)
+    n, c, h, w = a.shape
+    y = torch.empty_like(skip)
+    with torch.cuda.device(dev):
+        _check(lib().cdan_op_upsample_add(dtype_code(dtype), _c_void_p(_stream(dev)), _ptr(a), _ptr(skip), n, c, h, w,
+                                          int(up), _ptr(y)), "op_upsample_add")
+    return y
+
+
+POSTPROC_OPS = {"enhance_contrast": 0, "enhance_color": 1, "sharpen": 2, "soft_denoise": 3}
+
+
+def postprocess(images: torch.Tensor, op: str, arg: float) -> torch.Tensor:
+    dev = images.device
+    x = _f32(images, dev)
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise RuntimeError("cdan_b200: post-processing expects [N,3,H,W]")
+    y = torch.empty_like(x)
+    n, _, h, w = x.shape
+    with torch.cuda.device(dev):
+        _check(lib().cdan_postprocess(_c_void_p(_stream(dev)), POSTPROC_OPS[op], float(arg), _ptr(x), _ptr(y), n, h, w),
+               "postprocess")
+    return y
+
+
+def psnr_ssim(pred: torch.Tensor, target: torch.Tensor) -> Tuple[float, float]:
+    dev = pred.device
+    p, t = _f32(pred, dev), _f32(target, dev)
+    n, c, h, w = p.shape
+    res = (ctypes.c_float * 2)()
+    with torch.cuda.device(dev):
+        _check(lib().cdan_psnr_ssim(_c_void_p(_stream(dev)), _ptr(p), _ptr(t), n, c, h, w, res), "psnr_ssim")
+    return float(res[0]), float(res[1])

@@ -1,0 +1,268 @@
+// CBAM attention (models/cbam.py:26-95) as HBM-bound kernels over NHWC activations.
+//   pass 1  pool_partial : per-(n,c) sum and max over a slab of pixels  (deterministic 2-stage reduction,
+//                          no float atomics -> bitwise repeatable like the reference under cudnn.deterministic)
+//   pass 2  gate_mlp     : finish the reduction, shared MLP on avg and max, sigmoid  -> gate[n][c]
+//   pass 3  compress     : per-pixel channel max / mean of x*gate (warp-shuffle reduction) -> comp[n,h,w,2]
+//   pass 4  spatial_gate : sigmoid(bn(conv7x7(comp)))                                  -> sgate[n,h,w]
+//   pass 5  apply        : out = ((x*gate)*sgate) [* dense]
+#include "kernels.cuh"
+
+namespace cdan {
+namespace {
+
+constexpr int kPoolPixelsPerBlock = 2048;
+
+template <typename T>
+__global__ void __launch_bounds__(256) pool_partial_kernel(const T* __restrict__ x, int ld, int C, int HW, int nblk,
+                                                            float* __restrict__ psum, float* __restrict__ pmax) {
+  extern __shared__ float red[];  // [npl][C] sums then [npl][C] maxes
+  const int vecs = C >> 3;
+  const int npl = 256 / vecs;  // pixel lanes
+  const int vc = threadIdx.x % vecs, pl = threadIdx.x / vecs;
+  const int blk = blockIdx.x, n = blockIdx.y;
+  const int chunk = (HW + nblk - 1) / nblk;
+  const int p0 = blk * chunk, p1 = min(HW, p0 + chunk);
+  float s[8], m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; m[j] = -INFINITY; }
+  if (pl < npl) {
+    const T* base = x + size_t(n) * HW * ld + vc * 8;
+    for (int p = p0 + pl; p < p1; p += npl) {
+      const F8 v = load8<T>(base + size_t(p) * ld);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += v.v[j]; m[j] = fmaxf(m[j], v.v[j]); }
+    }
+    float* rs = red + (pl * C + vc * 8);
+    float* rm = red + (npl * C) + (pl * C + vc * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { rs[j] = s[j]; rm[j] = m[j]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float ss = 0.f, mm = -INFINITY;
+    for (int q = 0; q < npl; ++q) {  // fixed order
+      ss += red[q * C + c];
+      mm = fmaxf(mm, red[npl * C + q * C + c]);
+    }
+    psum[(size_t(n) * nblk + blk) * C + c] = ss;
+    pmax[(size_t(n) * nblk + blk) * C + c] = mm;
+  }
+}
+
+// One block per image.  att = mlp(avg) + mlp(max), mlp = Linear(C,C/16) -> ReLU -> Linear(C/16,C)
+// (models/cbam.py:30-35,41-45,54-57: the second bias is added once per pooled branch).
+__global__ void __launch_bounds__(256) gate_mlp_kernel(const float* __restrict__ psum, const float* __restrict__ pmax,
+                                                        int nblk, int C, int HW, const float* __restrict__ w1,
+                                                        const float* __restrict__ b1, const float* __restrict__ w2,
+                                                        const float* __restrict__ b2, float* __restrict__ gate) {
+  extern __shared__ float sm[];  // avg[C], mx[C], h_avg[R], h_max[R]
+  const int R = C / 16;
+  float* avg = sm;
+  float* mx = sm + C;
+  float* ha = sm + 2 * C;
+  float* hm = ha + R;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float ss = 0.f, mm = -INFINITY;
+    for (int b = 0; b < nblk; ++b) {
+      ss += psum[(size_t(n) * nblk + b) * C + c];
+      mm = fmaxf(mm, pmax[(size_t(n) * nblk + b) * C + c]);
+    }
+    avg[c] = ss / float(HW);
+    mx[c] = mm;
+  }
+  __syncthreads();
+  // hidden layer: one warp per hidden unit (round-robin), lanes stride over C
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarp = blockDim.x / 32;
+  for (int r = warp; r < R; r += nwarp) {
+    float da = 0.f, dm = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float w = w1[r * C + c];
+      da = fmaf(w, avg[c], da);
+      dm = fmaf(w, mx[c], dm);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      da += __shfl_xor_sync(0xffffffffu, da, o);
+      dm += __shfl_xor_sync(0xffffffffu, dm, o);
+    }
+    if (lane == 0) {
+      ha[r] = fmaxf(da + b1[r], 0.f);
+      hm[r] = fmaxf(dm + b1[r], 0.f);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float oa = b2[c], om = b2[c];
+    for (int r = 0; r < R; ++r) {
+      const float w = w2[c * R + r];
+      oa = fmaf(w, ha[r], oa);
+      om = fmaf(w, hm[r], om);
+    }
+    gate[size_t(n) * C + c] = 1.0f / (1.0f + expf(-(oa + om)));
+  }
+}
+
+// ChannelPool of the channel-gated tensor (models/cbam.py:68-70): comp[...,0] = max_c, comp[...,1] = mean_c.
+template <typename T>
+__global__ void __launch_bounds__(256) compress_kernel(const T* __restrict__ x, int ld, int C, int HW, size_t npix,
+                                                        const float* __restrict__ gate, float* __restrict__ comp) {
+  const int vecs = C >> 3;
+  const int lpp = vecs < 32 ? vecs : 32;  // lanes per pixel (power of two: C in {64,...,512})
+  const int ppw = 32 / lpp;               // pixels per warp
+  const int lane = threadIdx.x % 32;
+  const int sub = lane % lpp, wp = lane / lpp;
+  const size_t warp_global = (blockIdx.x * size_t(blockDim.x) + threadIdx.x) / 32;
+  const size_t nwarps = size_t(gridDim.x) * blockDim.x / 32;
+  for (size_t p0 = warp_global * ppw; p0 < npix; p0 += nwarps * ppw) {
+    const size_t pix = p0 + wp;
+    float mx = -INFINITY, sum = 0.f;
+    if (pix < npix) {
+      const int n = int(pix / HW);
+      const T* px = x + pix * ld;
+      const float* g = gate + size_t(n) * C;
+      for (int v = sub; v < vecs; v += lpp) {
+        const F8 a = load8<T>(px + v * 8);
+        const float4 g0 = *reinterpret_cast<const float4*>(g + v * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(g + v * 8 + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = a.v[j] * gg[j];
+          mx = fmaxf(mx, t);
+          sum += t;
+        }
+      }
+    }
+    for (int o = lpp >> 1; o > 0; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if (sub == 0 && pix < npix) {
+      comp[pix * 2 + 0] = mx;
+      comp[pix * 2 + 1] = sum / float(C);
+    }
+  }
+}
+
+// SpatialGate (models/cbam.py:72-82): 7x7 conv over the 2-channel map, zero pad 3, no bias, BN(1), sigmoid.
+__global__ void __launch_bounds__(256) spatial_gate_kernel(const float* __restrict__ comp, const float* __restrict__ w7,
+                                                            float bn_a, float bn_b, float* __restrict__ sgate, int N,
+                                                            int H, int W) {
+  __shared__ float w[98];
+  if (threadIdx.x < 98) w[threadIdx.x] = w7[threadIdx.x];
+  __syncthreads();
+  const size_t total = size_t(N) * H * W;
+  for (size_t pix = blockIdx.x * size_t(blockDim.x) + threadIdx.x; pix < total; pix += size_t(gridDim.x) * blockDim.x) {
+    const int x = int(pix % W), y = int((pix / W) % H);
+    const size_t nb = pix - (size_t(y) * W + x);
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      const int yy = y + r - 3;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 7; ++s) {
+        const int xx = x + s - 3;
+        if (xx < 0 || xx >= W) continue;
+        const float2 c = *reinterpret_cast<const float2*>(comp + (nb + size_t(yy) * W + xx) * 2);
+        acc = fmaf(w[r * 7 + s], c.x, acc);
+        acc = fmaf(w[49 + r * 7 + s], c.y, acc);
+      }
+    }
+    sgate[pix] = 1.0f / (1.0f + expf(-(bn_a * acc + bn_b)));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) apply_kernel(const T* __restrict__ x, int ld, const float* __restrict__ gate,
+                                                     const float* __restrict__ sgate, const T* __restrict__ mul,
+                                                     int mul_ld, T* __restrict__ out, int out_ld, int C, int HW,
+                                                     size_t npix) {
+  const int vecs = C >> 3;
+  const size_t total = npix * vecs;
+  for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total; idx += size_t(gridDim.x) * blockDim.x) {
+    const int v = int(idx % vecs);
+    const size_t pix = idx / vecs;
+    const int n = int(pix / HW);
+    const F8 a = load8<T>(x + pix * ld + v * 8);
+    const float* g = gate + size_t(n) * C + v * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(g);
+    const float4 g1 = *reinterpret_cast<const float4*>(g + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float sg = sgate[pix];
+    F8 r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r.v[j] = (a.v[j] * gg[j]) * sg;
+    if (mul) {
+      const F8 m = load8<T>(mul + pix * mul_ld + v * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r.v[j] *= m.v[j];
+    }
+    store8<T>(out + pix * out_ld + v * 8, r);
+  }
+}
+
+inline int grid_for(size_t total, int block = 256, int cap = 148 * 16) {
+  size_t g = (total + block - 1) / block;
+  return int(g < 1 ? 1 : (g > size_t(cap) ? cap : g));
+}
+
+template <typename T>
+int cbam_typed(const void* x, int x_ld, const void* mul, int mul_ld, void* out, int out_ld, int N, int H, int W, int C,
+               const CbamWeights& wt, const CbamScratch& sc, cudaStream_t s) {
+  const int HW = H * W;
+  const size_t npix = size_t(N) * HW;
+  const int vecs = C / 8;
+  const int npl = 256 / vecs;
+  pool_partial_kernel<T><<<dim3(sc.nblk, N), 256, 2 * npl * C * sizeof(float), s>>>((const T*)x, x_ld, C, HW, sc.nblk,
+                                                                                  sc.psum, sc.pmax);
+  CDAN_CUDA_OK(cudaGetLastError());
+  gate_mlp_kernel<<<N, 256, (2 * C + 2 * (C / 16)) * sizeof(float), s>>>(sc.psum, sc.pmax, sc.nblk, C, HW, wt.w1, wt.b1,
+                                                                         wt.w2, wt.b2, sc.gate);
+  CDAN_CUDA_OK(cudaGetLastError());
+  const int lpp = vecs < 32 ? vecs : 32;
+  compress_kernel<T><<<grid_for(npix * lpp), 256, 0, s>>>((const T*)x, x_ld, C, HW, npix, sc.gate, sc.comp);
+  CDAN_CUDA_OK(cudaGetLastError());
+  spatial_gate_kernel<<<grid_for(npix), 256, 0, s>>>(sc.comp, wt.w7, wt.bn_a, wt.bn_b, sc.sgate, N, H, W);
+  CDAN_CUDA_OK(cudaGetLastError());
+  apply_kernel<T><<<grid_for(npix * vecs), 256, 0, s>>>((const T*)x, x_ld, sc.gate, sc.sgate, (const T*)mul, mul_ld,
+                                                        (T*)out, out_ld, C, HW, npix);
+  CDAN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int cbam_pool_blocks(int HW) {
+  int b = (HW + kPoolPixelsPerBlock - 1) / kPoolPixelsPerBlock;
+  return b < 1 ? 1 : b;
+}
+
+size_t cbam_scratch_floats(int N, int C, int H, int W) {
+  const size_t nblk = cbam_pool_blocks(H * W);
+  return 2 * size_t(N) * nblk * C + size_t(N) * C + 3 * size_t(N) * H * W + 64;
+}
+
+void cbam_scratch_carve(float* base, int N, int C, int H, int W, CbamScratch* sc) {
+  sc->nblk = cbam_pool_blocks(H * W);
+  const size_t part = size_t(N) * sc->nblk * C;
+  sc->psum = base;
+  sc->pmax = base + part;
+  sc->gate = sc->pmax + part;
+  size_t off = 2 * part + size_t(N) * C;
+  off = (off + 3) / 4 * 4;  // 16-byte alignment for the float2 reads of comp
+  sc->comp = base + off;
+  sc->sgate = sc->comp + 2 * size_t(N) * H * W;
+}
+
+int cbam_launch(DType dt, const void* x, int x_ld, const void* mul, int mul_ld, void* out, int out_ld, int N, int H,
+                int W, int C, const CbamWeights& wt, const CbamScratch& sc, cudaStream_t s) {
+  if (C % 64 != 0 || C > 2048) return fail("cbam: gate_channels must be a multiple of 64 (<= 2048) for the CUDA path");
+  if ((C & (C - 1)) != 0) return fail("cbam: gate_channels must be a power of two for the CUDA path");
+  if (N > 65535) return fail("cbam: batch too large for one launch");
+  return dt == kF32 ? cbam_typed<float>(x, x_ld, mul, mul_ld, out, out_ld, N, H, W, C, wt, sc, s)
+                    : cbam_typed<bf16>(x, x_ld, mul, mul_ld, out, out_ld, N, H, W, C, wt, sc, s);
+}
+
+}  // namespace cdan

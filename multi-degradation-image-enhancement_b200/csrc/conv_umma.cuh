@@ -1,0 +1,17 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution, bf16 operands, fp32 accumulation in TMEM.
+#pragma once
+#include "conv.cuh"
+
+namespace cdan {
+
+struct UmmaPack;  // device-resident, pre-swizzled bf16 weight image + fp32 bias
+
+// Build from the CUDA-core packing (fp32 [taps][Cin][CoutP], BN already folded) — host pointers.
+int umma_pack_create(const float* w_taps_cin_coutp, const float* bias_coutp, int Cin, int Cout, int CoutP, int ks,
+                     UmmaPack** out);
+void umma_pack_destroy(UmmaPack* p);
+
+bool conv_umma_supported(const ConvDesc& d);
+int conv_umma_launch(const ConvDesc& d, const UmmaPack& pack, cudaStream_t stream);
+
+}  // namespace cdan

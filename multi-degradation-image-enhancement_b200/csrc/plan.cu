@@ -1,0 +1,494 @@
+// C-ABI entry points: plan life cycle, weight folding/packing, the CDAN forward schedule, stage taps.
+#include "plan.hpp"
+
+#include <cmath>
+#include <cstring>
+
+#include "../../include/cdan_b200.h"
+
+namespace cdan {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+int fail(const std::string& msg) {
+  g_error = msg;
+  return -1;
+}
+
+namespace {
+
+constexpr double kBnEps = 1e-5;  // nn.BatchNorm2d default eps (models/cdan.py:12; models/cbam.py:11)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+using HostDict = std::map<std::string, std::vector<float>>;
+
+int need(const HostDict& sd, const std::string& key, size_t numel, const float** out) {
+  auto it = sd.find(key);
+  if (it == sd.end()) return fail("state_dict is missing key '" + key + "'");
+  if (it->second.size() != numel)
+    return fail("state_dict key '" + key + "' has " + std::to_string(it->second.size()) + " elements, expected " +
+                std::to_string(numel));
+  *out = it->second.data();
+  return 0;
+}
+
+// eval-mode BatchNorm as y = s*x + t
+int bn_affine(const HostDict& sd, const std::string& prefix, int C, std::vector<double>& s, std::vector<double>& t) {
+  const float *g, *b, *m, *v;
+  CDAN_TRY(need(sd, prefix + ".weight", C, &g));
+  CDAN_TRY(need(sd, prefix + ".bias", C, &b));
+  CDAN_TRY(need(sd, prefix + ".running_mean", C, &m));
+  CDAN_TRY(need(sd, prefix + ".running_var", C, &v));
+  s.resize(C);
+  t.resize(C);
+  for (int c = 0; c < C; ++c) {
+    s[c] = double(g[c]) / std::sqrt(double(v[c]) + kBnEps);
+    t[c] = double(b[c]) - double(m[c]) * s[c];
+  }
+  return 0;
+}
+
+int upload(cdan_plan* p, const std::vector<float>& h, float** d) {
+  CDAN_CUDA_OK(cudaMalloc(d, h.size() * sizeof(float)));
+  p->owned.push_back(*d);
+  CDAN_CUDA_OK(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// Pack one convolution for the CUDA-core kernel: fp32 [taps][CinPhys][CoutP].
+//   w         : Conv2d weight [Cout][Cin][ks][ks], or ConvTranspose2d weight [Cin][Cout][ks][ks] when `transposed`
+//               (then the equivalent correlation kernel is W'[o][i][u][v] = W[i][o][ks-1-u][ks-1-v])
+//   post_s/t  : per-output-channel affine of a FOLLOWING BatchNorm (folded into weight and bias), may be empty
+//   cmap      : logical input channel -> physical channel of the NHWC buffer
+int pack_conv(cdan_plan* p, ConvLayer& L, const float* w, const float* bias, int Cout, int CinLogical, int ks,
+              bool transposed, const std::vector<double>& post_s, const std::vector<double>& post_t,
+              const std::vector<int>& cmap, int CinPhys) {
+  L.Cin = CinPhys;
+  L.Cout = Cout;
+  L.ks = ks;
+  L.CoutP = int(align_up(size_t(Cout), 16));
+  const int taps = ks * ks;
+  std::vector<float> hw(size_t(taps) * CinPhys * L.CoutP, 0.f), hb(L.CoutP, 0.f);
+  for (int o = 0; o < Cout; ++o) {
+    const double s = post_s.empty() ? 1.0 : post_s[o];
+    for (int ci = 0; ci < CinLogical; ++ci)
+      for (int u = 0; u < ks; ++u)
+        for (int v = 0; v < ks; ++v) {
+          const double val = transposed ? w[((size_t(ci) * Cout + o) * ks + (ks - 1 - u)) * ks + (ks - 1 - v)]
+                                        : w[((size_t(o) * CinLogical + ci) * ks + u) * ks + v];
+          hw[(size_t(u * ks + v) * CinPhys + cmap[ci]) * L.CoutP + o] = float(val * s);
+        }
+    hb[o] = float(post_s.empty() ? double(bias[o]) : double(bias[o]) * s + post_t[o]);
+  }
+  CDAN_TRY(upload(p, hw, &L.d_w));
+  CDAN_TRY(upload(p, hb, &L.d_bias));
+  return 0;
+}
+
+int pack_pre(cdan_plan* p, ConvLayer& L, const std::vector<double>& s, const std::vector<double>& t,
+             const std::vector<int>& cmap, int CinPhys) {
+  std::vector<float> hs(CinPhys, 0.f), ht(CinPhys, 0.f);  // pad channels: relu(0*x + 0) = 0
+  for (size_t c = 0; c < s.size(); ++c) {
+    hs[cmap[c]] = float(s[c]);
+    ht[cmap[c]] = float(t[c]);
+  }
+  CDAN_TRY(upload(p, hs, &L.d_pre_s));
+  CDAN_TRY(upload(p, ht, &L.d_pre_t));
+  return 0;
+}
+
+std::vector<int> dense_cmap(int C, int Cpad, int n_logical) {
+  std::vector<int> m(n_logical);
+  for (int j = 0; j < n_logical; ++j) m[j] = j < C ? j : Cpad + (j - C);
+  return m;
+}
+
+int load_conv_block(cdan_plan* p, const HostDict& sd, ConvId id, const std::string& prefix, int Ci, int Co) {
+  const float *w, *b;
+  CDAN_TRY(need(sd, prefix + ".conv.weight", size_t(Co) * Ci * 9, &w));
+  CDAN_TRY(need(sd, prefix + ".conv.bias", Co, &b));
+  std::vector<double> s, t;
+  CDAN_TRY(bn_affine(sd, prefix + ".bn", Co, s, t));
+  ConvLayer& L = p->conv[id];
+  L.name = prefix;
+  L.relu = 1;
+  return pack_conv(p, L, w, b, Co, Ci, 3, false, s, t, dense_cmap(Ci, Ci, Ci), Ci);
+}
+
+int load_dense_block(cdan_plan* p, const HostDict& sd, ConvId first, const std::string& prefix, int C, int Cpad,
+                     int Cout) {
+  for (int l = 0; l < 4; ++l) {
+    const int ci = C + 16 * l, ciPhys = Cpad + 16 * l;
+    const std::string lp = prefix + ".layers." + std::to_string(l);
+    const float *w, *b;
+    CDAN_TRY(need(sd, lp + ".2.weight", size_t(16) * ci * 9, &w));
+    CDAN_TRY(need(sd, lp + ".2.bias", 16, &b));
+    std::vector<double> s, t;
+    CDAN_TRY(bn_affine(sd, lp + ".0", ci, s, t));
+    ConvLayer& L = p->conv[first + l];
+    L.name = lp;
+    L.relu = 0;
+    const std::vector<int> cmap = dense_cmap(C, Cpad, ci);
+    CDAN_TRY(pack_conv(p, L, w, b, 16, ci, 3, false, {}, {}, cmap, ciPhys));
+    CDAN_TRY(pack_pre(p, L, s, t, cmap, ciPhys));
+  }
+  const int ci = C + 64, ciPhys = Cpad + 64;
+  const std::string tp = prefix + ".transition_layer";
+  const float *w, *b;
+  CDAN_TRY(need(sd, tp + ".2.weight", size_t(Cout) * ci, &w));
+  CDAN_TRY(need(sd, tp + ".2.bias", Cout, &b));
+  std::vector<double> s, t;
+  CDAN_TRY(bn_affine(sd, tp + ".0", ci, s, t));
+  ConvLayer& L = p->conv[first + 4];
+  L.name = tp;
+  L.relu = 0;
+  const std::vector<int> cmap = dense_cmap(C, Cpad, ci);
+  CDAN_TRY(pack_conv(p, L, w, b, Cout, ci, 1, false, {}, {}, cmap, ciPhys));
+  CDAN_TRY(pack_pre(p, L, s, t, cmap, ciPhys));
+  return 0;
+}
+
+int load_decoder_conv(cdan_plan* p, const HostDict& sd, ConvId id, int idx, int Ci, int Co) {
+  const std::string cp = "decoder.conv" + std::to_string(idx), bp = "decoder.bn" + std::to_string(idx);
+  const float *w, *b;
+  CDAN_TRY(need(sd, cp + ".weight", size_t(Ci) * Co * 9, &w));
+  CDAN_TRY(need(sd, cp + ".bias", Co, &b));
+  std::vector<double> s, t;
+  CDAN_TRY(bn_affine(sd, bp, Co, s, t));
+  ConvLayer& L = p->conv[id];
+  L.name = cp;
+  L.relu = 1;
+  return pack_conv(p, L, w, b, Co, Ci, 3, true, s, t, dense_cmap(Ci, Ci, Ci), Ci);
+}
+
+int load_cbam(cdan_plan* p, const HostDict& sd, int slot, const std::string& prefix, int C) {
+  const int R = C / 16;
+  const float *w1, *b1, *w2, *b2, *w7;
+  CDAN_TRY(need(sd, prefix + ".ChannelGate.mlp.1.weight", size_t(R) * C, &w1));
+  CDAN_TRY(need(sd, prefix + ".ChannelGate.mlp.1.bias", R, &b1));
+  CDAN_TRY(need(sd, prefix + ".ChannelGate.mlp.3.weight", size_t(C) * R, &w2));
+  CDAN_TRY(need(sd, prefix + ".ChannelGate.mlp.3.bias", C, &b2));
+  CDAN_TRY(need(sd, prefix + ".SpatialGate.spatial.conv.weight", 98, &w7));
+  std::vector<double> s, t;
+  CDAN_TRY(bn_affine(sd, prefix + ".SpatialGate.spatial.bn", 1, s, t));
+  CbamLayer& L = p->cbam[slot];
+  L.C = C;
+  float* d;
+  CDAN_TRY(upload(p, std::vector<float>(w1, w1 + size_t(R) * C), &d)); L.w.w1 = d;
+  CDAN_TRY(upload(p, std::vector<float>(b1, b1 + R), &d)); L.w.b1 = d;
+  CDAN_TRY(upload(p, std::vector<float>(w2, w2 + size_t(C) * R), &d)); L.w.w2 = d;
+  CDAN_TRY(upload(p, std::vector<float>(b2, b2 + C), &d)); L.w.b2 = d;
+  CDAN_TRY(upload(p, std::vector<float>(w7, w7 + 98), &d)); L.w.w7 = d;
+  L.w.bn_a = float(s[0]);
+  L.w.bn_b = float(t[0]);
+  return 0;
+}
+
+void free_weights(cdan_plan* p) {
+  for (void* d : p->owned) cudaFree(d);
+  p->owned.clear();
+  for (auto& L : p->conv) L = ConvLayer{};
+  p->loaded = false;
+}
+
+// ------------------------------------------------------------------------------------------ workspace
+size_t carve(Buffers& b, char* base, DType dt, int N, int H, int W) {
+  const size_t es = dt == kF32 ? 4 : 2;
+  const size_t p1 = size_t(N) * H * W, p2 = p1 / 4, p4 = p1 / 16, p8 = p1 / 64;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* r = base ? base + off : nullptr;
+    off += align_up(bytes, 1024);
+    return r;
+  };
+  b.D1 = take(p2 * 128 * es);
+  b.DN1 = take(p2 * 64 * es);
+  b.D2 = take(p4 * 192 * es);
+  b.DN2 = take(p4 * 128 * es);
+  b.D3 = take(p8 * 320 * es);
+  b.DN3 = take(p8 * 256 * es);
+  b.E4 = take(p8 * 512 * es);
+  b.B0 = take(p8 * 512 * es);
+  b.T1 = take(p8 * 256 * es);
+  b.A1 = take(p8 * 256 * es);
+  b.C1 = take(p8 * 256 * es);
+  b.T2 = take(p8 * 128 * es);
+  b.U2 = take(p4 * 128 * es);
+  b.C2 = take(p4 * 128 * es);
+  b.T3 = take(p4 * 64 * es);
+  b.U3 = take(p2 * 64 * es);
+  b.C3 = take(p2 * 64 * es);
+  b.T4 = take(p2 * 8 * es);
+  b.FD = take(p1 * 80 * es);
+  size_t sc = 0;
+  sc = std::max(sc, cbam_scratch_floats(N, 512, H / 8, W / 8));
+  sc = std::max(sc, cbam_scratch_floats(N, 256, H / 8, W / 8));
+  sc = std::max(sc, cbam_scratch_floats(N, 128, H / 4, W / 4));
+  sc = std::max(sc, cbam_scratch_floats(N, 64, H / 2, W / 2));
+  b.cbam_scratch = (float*)take(sc * sizeof(float));
+  b.x_dev = (float*)take(p1 * 3 * sizeof(float));
+  b.y_dev = (float*)take(p1 * 3 * sizeof(float));
+  b.total_bytes = off;
+  return off;
+}
+
+int ensure_workspace(cdan_plan* p, int N, int H, int W) {
+  Buffers probe{};
+  const size_t bytes = carve(probe, nullptr, p->dt, N, H, W);
+  if (bytes > p->ws_bytes) {
+    if (p->ws) CDAN_CUDA_OK(cudaFree(p->ws));
+    p->ws = nullptr;
+    p->ws_bytes = 0;
+    CDAN_CUDA_OK(cudaMalloc(&p->ws, bytes));
+    p->ws_bytes = bytes;
+  }
+  carve(p->buf, (char*)p->ws, p->dt, N, H, W);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ schedule
+int conv_dispatch(cdan_plan* p, const ConvDesc& d, cudaStream_t s);  // below
+
+int run_conv(cdan_plan* p, ConvId id, int N, int H, int W, const void* in, int in_ld, void* out, int out_ld,
+             int pool, cudaStream_t s, const float* in_nchw = nullptr, float* out_nchw = nullptr, int sigmoid = 0) {
+  const ConvLayer& L = p->conv[id];
+  ConvDesc d;
+  d.N = N; d.H = H; d.W = W;
+  d.Cin = L.Cin; d.Cout = L.Cout; d.ks = L.ks;
+  d.in = in; d.in_ld = in_ld; d.in_nchw = in_nchw;
+  d.pre_scale = L.d_pre_s; d.pre_shift = L.d_pre_t;
+  d.w = L.d_w; d.CoutP = L.CoutP; d.bias = L.d_bias;
+  d.relu = L.relu; d.pool = pool;
+  d.out = out; d.out_ld = out_ld; d.out_nchw = out_nchw; d.sigmoid = sigmoid;
+  CDAN_TRY(conv_dispatch(p, d, s));
+  p->launches += 1;
+  return 0;
+}
+
+int conv_dispatch(cdan_plan* p, const ConvDesc& d, cudaStream_t s) {
+  return conv_simt_launch(d, p->dt, s);
+}
+
+inline char* at(void* base, size_t elems, DType dt) { return (char*)base + elems * (dt == kF32 ? 4 : 2); }
+
+int run_dense(cdan_plan* p, ConvId first, int N, int h, int w, void* D, int ld, int Cpad, void* DN, int Cout,
+              cudaStream_t s, float* out_nchw = nullptr) {
+  for (int l = 0; l < 4; ++l)
+    CDAN_TRY(run_conv(p, ConvId(first + l), N, h, w, D, ld, at(D, Cpad + 16 * l, p->dt), ld, 0, s));
+  (void)Cout;
+  return run_conv(p, ConvId(first + 4), N, h, w, D, ld, DN, DN ? p->conv[first + 4].Cout : 0, 0, s, nullptr, out_nchw,
+                  out_nchw ? 1 : 0);
+}
+
+int run_cbam(cdan_plan* p, int slot, const void* x, const void* mul, void* out, int N, int h, int w, cudaStream_t s) {
+  const CbamLayer& L = p->cbam[slot];
+  CbamScratch sc;
+  cbam_scratch_carve(p->buf.cbam_scratch, N, L.C, h, w, &sc);
+  CDAN_TRY(cbam_launch(p->dt, x, L.C, mul, L.C, out, L.C, N, h, w, L.C, L.w, sc, s));
+  p->launches += 5;
+  return 0;
+}
+
+int forward_impl(cdan_plan* p, cudaStream_t s, const float* x, float* y, int N, int H, int W) {
+  if (!p->loaded) return fail("cdan_forward: no weights loaded (call cdan_plan_load_weights first)");
+  if (N <= 0 || H <= 0 || W <= 0) return fail("cdan_forward: empty input");
+  if (H % 8 || W % 8)
+    return fail("cdan_forward: H and W must be multiples of 8 (got " + std::to_string(H) + "x" + std::to_string(W) +
+                "); the reference fails with a size mismatch for such inputs (models/cdan.py:75-89,137-154)");
+  CDAN_TRY(ensure_workspace(p, N, H, W));
+  Buffers& b = p->buf;
+  const DType dt = p->dt;
+  const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8;
+  p->launches = 0;
+  p->N = N; p->H = H; p->W = W;
+
+  // ---- Encoder (models/cdan.py:70-98).  Pooled ConvBlock outputs land in channels [0,C) of the dense-block
+  //      concat buffers, so they double as skip connections and as the first `features` entry.
+  CDAN_TRY(run_conv(p, ENC1, N, H, W, nullptr, 0, b.D1, 128, 1, s, x));
+  CDAN_TRY(run_dense(p, D1L0, N, H2, W2, b.D1, 128, 64, b.DN1, 64, s));
+  CDAN_TRY(run_conv(p, ENC2, N, H2, W2, b.D1, 128, b.D2, 192, 1, s));
+  CDAN_TRY(run_dense(p, D2L0, N, H4, W4, b.D2, 192, 128, b.DN2, 128, s));
+  CDAN_TRY(run_conv(p, ENC3, N, H4, W4, b.D2, 192, b.D3, 320, 1, s));
+  CDAN_TRY(run_dense(p, D3L0, N, H8, W8, b.D3, 320, 256, b.DN3, 256, s));
+  CDAN_TRY(run_conv(p, ENC4, N, H8, W8, b.D3, 320, b.E4, 512, 0, s));
+  // ---- bottleneck CBAM(512) (models/cdan.py:173)
+  CDAN_TRY(run_cbam(p, 0, b.E4, nullptr, b.B0, N, H8, W8, s));
+  // ---- Decoder (models/cdan.py:126-159)
+  CDAN_TRY(run_conv(p, DEC1, N, H8, W8, b.B0, 512, b.T1, 256, 0, s));
+  CDAN_TRY(up_add_launch(dt, b.T1, 256, b.D3, 320, b.A1, 256, N, H8, W8, 256, 0, s));
+  CDAN_TRY(run_cbam(p, 1, b.A1, b.DN3, b.C1, N, H8, W8, s));
+  CDAN_TRY(run_conv(p, DEC2, N, H8, W8, b.C1, 256, b.T2, 128, 0, s));
+  CDAN_TRY(up_add_launch(dt, b.T2, 128, b.D2, 192, b.U2, 128, N, H4, W4, 128, 1, s));
+  CDAN_TRY(run_cbam(p, 2, b.U2, b.DN2, b.C2, N, H4, W4, s));
+  CDAN_TRY(run_conv(p, DEC3, N, H4, W4, b.C2, 128, b.T3, 64, 0, s));
+  CDAN_TRY(up_add_launch(dt, b.T3, 64, b.D1, 128, b.U3, 64, N, H2, W2, 64, 1, s));
+  CDAN_TRY(run_cbam(p, 3, b.U3, b.DN1, b.C3, N, H2, W2, s));
+  CDAN_TRY(run_conv(p, DEC4, N, H2, W2, b.C3, 64, b.T4, 8, 0, s));
+  CDAN_TRY(up_add_input_launch(dt, b.T4, 8, x, b.FD, 80, 16, N, H, W, s));
+  p->launches += 4;
+  // final DenseBlock(3,3,16,4) + sigmoid, written straight to the caller's fp32 NCHW output
+  CDAN_TRY(run_dense(p, FDL0, N, H, W, b.FD, 80, 16, nullptr, 3, s, y));
+
+  auto& st = p->stages;
+  st.clear();
+  st["enc.out1"] = {b.D1, 64, 128, H2, W2};
+  st["enc.dense1"] = {b.DN1, 64, 64, H2, W2};
+  st["enc.out2"] = {b.D2, 128, 192, H4, W4};
+  st["enc.dense2"] = {b.DN2, 128, 128, H4, W4};
+  st["enc.out3"] = {b.D3, 256, 320, H8, W8};
+  st["enc.dense3"] = {b.DN3, 256, 256, H8, W8};
+  st["enc.conv4"] = {b.E4, 512, 512, H8, W8};
+  st["bottleneck"] = {b.B0, 512, 512, H8, W8};
+  st["dec.bn1"] = {b.T1, 256, 256, H8, W8};
+  st["dec.gated1"] = {b.C1, 256, 256, H8, W8};
+  st["dec.bn2"] = {b.T2, 128, 128, H8, W8};
+  st["dec.gated2"] = {b.C2, 128, 128, H4, W4};
+  st["dec.bn3"] = {b.T3, 64, 64, H4, W4};
+  st["dec.gated3"] = {b.C3, 64, 64, H2, W2};
+  st["dec.bn4"] = {b.T4, 3, 8, H2, W2};
+  st["dec.final_in"] = {b.FD, 3, 80, H, W};
+  return 0;
+}
+
+}  // namespace
+}  // namespace cdan
+
+using namespace cdan;
+
+extern "C" {
+
+const char* cdan_last_error(void) { return g_error.c_str(); }
+const char* cdan_version(void) { return "cdan_b200 0.1 sm_100a"; }
+
+int cdan_plan_create(int device, int dtype, cdan_plan** plan_out) {
+  if (!plan_out) return fail("cdan_plan_create: plan_out is NULL");
+  if (dtype != CDAN_DTYPE_F32 && dtype != CDAN_DTYPE_BF16) return fail("cdan_plan_create: unknown dtype");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(std::string("cdan_plan_create: no CUDA device available (") + cudaGetErrorString(e) +
+                "); this library has no CPU fallback");
+  if (device < 0 || device >= count) return fail("cdan_plan_create: device index out of range");
+  cudaDeviceProp prop;
+  CDAN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(std::string("cdan_plan_create: built for sm_100a (B200) only, device is sm_") +
+                std::to_string(prop.major) + std::to_string(prop.minor));
+  cdan_plan* p = new cdan_plan();
+  p->device = device;
+  p->dt = DType(dtype);
+  *plan_out = p;
+  return 0;
+}
+
+int cdan_plan_destroy(cdan_plan* p) {
+  if (!p) return 0;
+  DeviceGuard g(p->device);
+  free_weights(p);
+  if (p->ws) cudaFree(p->ws);
+  if (p->own_stream) cudaStreamDestroy(p->own_stream);
+  delete p;
+  return 0;
+}
+
+int cdan_plan_set_option(cdan_plan* p, const char* name, int value) {
+  if (!p || !name) return fail("cdan_plan_set_option: NULL argument");
+  if (!strcmp(name, "conv_impl")) {
+    if (value < 0 || value > 1) return fail("conv_impl must be 0 (auto) or 1 (CUDA cores)");
+    p->conv_impl = value;
+    return 0;
+  }
+  return fail(std::string("unknown option '") + name + "'");
+}
+
+int cdan_plan_load_weights(cdan_plan* p, int n, const char* const* keys, const void* const* ptrs,
+                           const int64_t* numels) {
+  if (!p || !keys || !ptrs || !numels) return fail("cdan_plan_load_weights: NULL argument");
+  DeviceGuard g(p->device);
+  HostDict sd;
+  for (int i = 0; i < n; ++i) {
+    const std::string key = keys[i];
+    const std::string tail = "num_batches_tracked";
+    if (key.size() >= tail.size() && key.compare(key.size() - tail.size(), tail.size(), tail) == 0) continue;
+    std::vector<float> h(static_cast<size_t>(numels[i]), 0.f);
+    CDAN_CUDA_OK(cudaMemcpy(h.data(), ptrs[i], h.size() * sizeof(float), cudaMemcpyDefault));
+    sd.emplace(key, std::move(h));
+  }
+  free_weights(p);
+  int rc = 0;
+  const int enc_c[5] = {3, 64, 128, 256, 512};
+  for (int i = 1; i <= 4 && !rc; ++i)
+    rc = load_conv_block(p, sd, ConvId(ENC1 + i - 1), "encoder.conv" + std::to_string(i), enc_c[i - 1], enc_c[i]);
+  if (!rc) rc = load_dense_block(p, sd, D1L0, "encoder.dense1", 64, 64, 64);
+  if (!rc) rc = load_dense_block(p, sd, D2L0, "encoder.dense2", 128, 128, 128);
+  if (!rc) rc = load_dense_block(p, sd, D3L0, "encoder.dense3", 256, 256, 256);
+  if (!rc) rc = load_dense_block(p, sd, FDL0, "decoder.final_dense", 3, 16, 3);
+  const int dec_c[5] = {512, 256, 128, 64, 3};
+  for (int i = 1; i <= 4 && !rc; ++i) rc = load_decoder_conv(p, sd, ConvId(DEC1 + i - 1), i, dec_c[i - 1], dec_c[i]);
+  if (!rc) rc = load_cbam(p, sd, 0, "bottleneck", 512);
+  if (!rc) rc = load_cbam(p, sd, 1, "decoder.cbam1", 256);
+  if (!rc) rc = load_cbam(p, sd, 2, "decoder.cbam2", 128);
+  if (!rc) rc = load_cbam(p, sd, 3, "decoder.cbam3", 64);
+  if (rc) {
+    free_weights(p);
+    return rc;
+  }
+  p->loaded = true;
+  return 0;
+}
+
+int cdan_workspace_bytes(cdan_plan* p, int N, int H, int W, size_t* bytes_out) {
+  if (!p || !bytes_out) return fail("cdan_workspace_bytes: NULL argument");
+  if (N <= 0 || H <= 0 || W <= 0 || H % 8 || W % 8) return fail("cdan_workspace_bytes: H and W must be positive multiples of 8");
+  Buffers b{};
+  *bytes_out = carve(b, nullptr, p->dt, N, H, W);
+  return 0;
+}
+
+int cdan_forward(cdan_plan* p, void* stream, const float* x, float* y, int N, int H, int W) {
+  if (!p || !x || !y) return fail("cdan_forward: NULL argument");
+  DeviceGuard g(p->device);
+  return forward_impl(p, (cudaStream_t)stream, x, y, N, H, W);
+}
+
+int cdan_forward_host(cdan_plan* p, const float* x_host, float* y_host, int N, int H, int W) {
+  if (!p || !x_host || !y_host) return fail("cdan_forward_host: NULL argument");
+  DeviceGuard g(p->device);
+  if (H % 8 || W % 8 || N <= 0) return fail("cdan_forward_host: H and W must be multiples of 8");
+  if (!p->own_stream) CDAN_CUDA_OK(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+  CDAN_TRY(ensure_workspace(p, N, H, W));
+  const size_t bytes = size_t(N) * 3 * H * W * sizeof(float);
+  CDAN_CUDA_OK(cudaMemcpyAsync(p->buf.x_dev, x_host, bytes, cudaMemcpyHostToDevice, p->own_stream));
+  CDAN_TRY(forward_impl(p, p->own_stream, p->buf.x_dev, p->buf.y_dev, N, H, W));
+  CDAN_CUDA_OK(cudaMemcpyAsync(y_host, p->buf.y_dev, bytes, cudaMemcpyDeviceToHost, p->own_stream));
+  CDAN_CUDA_OK(cudaStreamSynchronize(p->own_stream));
+  return 0;
+}
+
+int cdan_stage_read(cdan_plan* p, void* stream, const char* name, float* dst, int64_t shape_out[4]) {
+  if (!p || !name) return fail("cdan_stage_read: NULL argument");
+  DeviceGuard g(p->device);
+  auto it = p->stages.find(name);
+  if (it == p->stages.end()) return fail(std::string("cdan_stage_read: unknown stage '") + name + "' (run cdan_forward first)");
+  const Stage& st = it->second;
+  if (shape_out) {
+    shape_out[0] = p->N; shape_out[1] = st.C; shape_out[2] = st.h; shape_out[3] = st.w;
+  }
+  if (!dst) return 0;
+  return nhwc_to_nchw_launch(p->dt, st.p, st.ld, dst, p->N, st.C, st.h, st.w, (cudaStream_t)stream);
+}
+
+int cdan_last_launch_count(cdan_plan* p) { return p ? p->launches : 0; }
+
+}  // extern "C"
