@@ -1,8 +1,576 @@
+// tcgen05 implicit-GEMM convolution for sm_100a (3x3 pad 1 / 1x1, stride 1, NHWC bf16, fp32 accumulate in TMEM).
+//
+// Formulation ("flattened shifted GEMM"): a CTA owns an output tile of TH rows x TW columns of one image.  The halo'd
+// input tile ((TH+2) x WP pixels, WP = TW+2) of one 64-channel K-chunk is staged ONCE in shared memory as
+// [pixel][64 ch] = 128-byte rows in the canonical K-major SWIZZLE_128B layout.  Because the swizzle is a function of
+// the absolute smem address (verified by csrc/probes/umma_probe.cu on B200), the A operand of tap (r,s) is simply the
+// same buffer viewed from row offset r*WP+s: nine descriptor offsets replace nine im2col loads.  Output "pixel"
+// p = hh*WP + ww lives in TMEM lane p%128 of M-block p/128; columns ww >= TW are garbage and masked in the epilogue.
+//
+// Warp roles (warp-specialised, mbarrier pipelines, persistent over tiles):
+//   warp 0      : producer — bulk-copies pre-swizzled weight blocks (B ring) and, in TMA mode, issues the 4-D
+//                 tensor-map tile loads of A (hardware zero fill = conv padding)
+//   warp 1      : tcgen05.mma issuer (one elected lane)
+//   warp 2      : TMEM allocator
+//   warps 4-7   : epilogue — tcgen05.ld, bias(+folded BN), ReLU, optional 2x2 max-pool / sigmoid+NCHW, global stores
+//   warps 8-15  : (producer modes only) A-tile builders: global load -> dense-block pre-activation
+//                 relu(s*x+t) in fp32 -> zero padding AFTER the activation -> swizzled st.shared, or the fp32 NCHW
+//                 3-channel network input -> bf16
 #include "conv_umma.cuh"
+
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "ptx_sm100.cuh"
+
 namespace cdan {
-struct UmmaPack { int dummy; };
-int umma_pack_create(const float*, const float*, int, int, int, int, UmmaPack** out) { *out = nullptr; return fail("tcgen05 conv not built yet"); }
-void umma_pack_destroy(UmmaPack*) {}
-bool conv_umma_supported(const ConvDesc&) { return false; }
-int conv_umma_launch(const ConvDesc&, const UmmaPack&, cudaStream_t) { return fail("tcgen05 conv not built yet"); }
+
+struct UmmaPack {
+  uint8_t* d_w = nullptr;   // [npass][chunk][tap][NT rows][128 B swizzled]
+  float* d_bias = nullptr;  // [npass*NT]
+  int Cin = 0, Cout = 0, ks = 3, NT = 0, npass = 1, nchunks = 0;
+};
+
+namespace {
+
+enum InMode : int { kInTma = 0, kInPro = 1, kInNchw3 = 2 };
+
+struct KParams {
+  int N, H, W, Cin, in_ld;
+  int ks, halo, taps;
+  int TH, TW, WP, NMB, NT;
+  int tiles_x, tiles_y, ntiles;  // ntiles = N*tiles_y*tiles_x (per N-pass)
+  int nchunks, npass, Cout;
+  int SA, SB, ACC;
+  int a_stage_bytes, b_stage_bytes, tps, bst_per_chunk;  // tps = taps per B stage
+  int a_rows;                                             // (TH+2*halo)*WP rows actually produced
+  int relu, pool, sigmoid;
+  const bf16* in;
+  const float* in_nchw;
+  const float* pre_s;
+  const float* pre_t;
+  const uint8_t* wpack;
+  const float* bias;
+  bf16* out;
+  int out_ld;
+  float* out_nchw;
+};
+
+constexpr int kMaxSA = 4, kMaxSB = 8;
+
+__device__ __forceinline__ void decode_tile(const KParams& P, int t, int& n, int& h0, int& w0) {
+  const int per_img = P.tiles_x * P.tiles_y;
+  n = t / per_img;
+  const int r = t - n * per_img;
+  const int ty = r / P.tiles_x;
+  h0 = ty * P.TH;
+  w0 = (r - ty * P.tiles_x) * P.TW;
 }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int IN_MODE>
+__global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap tmapA, const KParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + size_t(P.SA) * P.a_stage_bytes;
+  uint8_t* sTail = sB + size_t(P.SB) * P.b_stage_bytes + 1024;  // 1 KB slack for garbage-row over-reads
+  float* s_bias = reinterpret_cast<float*>(sTail);                // [NT]
+  float* s_xbuf = s_bias + 256;                                   // pool exchange: [2][2 warps][32 lanes][32 cols]
+
+  __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], b_full[kMaxSB], b_empty[kMaxSB], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int total_work = P.ntiles * P.npass;
+  constexpr int kProducerWarps = 8;
+
+  if (tid == 0) {
+    for (int i = 0; i < P.SA; ++i) {
+      ptx::mbar_init(&a_full[i], IN_MODE == kInTma ? 1 : kProducerWarps);
+      ptx::mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < P.SB; ++i) {
+      ptx::mbar_init(&b_full[i], 1);
+      ptx::mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&acc_full[i], 1);
+      ptx::mbar_init(&acc_empty[i], 4);
+    }
+    ptx::fence_mbar_init();
+    if (IN_MODE == kInTma) ptx::prefetch_tmap(&tmapA);
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(&tmem_base_s, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ============================================================ producer: B ring (+ A via TMA)
+    if (lane == 0) {
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int t = work / P.npass, pass = work - t * P.npass;
+        int n, h0, w0;
+        decode_tile(P, t, n, h0, w0);
+        for (int c = 0; c < P.nchunks; ++c) {
+          if (IN_MODE == kInTma) {
+            ptx::mbar_wait(&a_empty[sa], pa ^ 1);
+            ptx::mbar_arrive_expect_tx(&a_full[sa], uint32_t(P.a_rows) * 128u);
+            ptx::tma_load_4d(sA + size_t(sa) * P.a_stage_bytes, &tmapA, c * 64, w0 - P.halo, h0 - P.halo, n,
+                             &a_full[sa]);
+            if (++sa == P.SA) { sa = 0; pa ^= 1; }
+          }
+          const uint8_t* wsrc = P.wpack + (size_t(pass) * P.nchunks + c) * P.taps * (size_t(P.NT) * 128);
+          for (int j = 0; j < P.bst_per_chunk; ++j) {
+            const int ntap = min(P.tps, P.taps - j * P.tps);
+            const uint32_t bytes = uint32_t(ntap) * P.NT * 128u;
+            ptx::mbar_wait(&b_empty[sb], pb ^ 1);
+            ptx::mbar_arrive_expect_tx(&b_full[sb], bytes);
+            ptx::bulk_g2s(sB + size_t(sb) * P.b_stage_bytes, wsrc + size_t(j) * P.tps * P.NT * 128, bytes, &b_full[sb]);
+            if (++sb == P.SB) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, P.NT);
+      const uint32_t sA_u = ptx::smem_u32(sA), sB_u = ptx::smem_u32(sB);
+      int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        ptx::mbar_wait(&acc_empty[as], pacc ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t acc_col = tmem_base + uint32_t(as * P.NMB * P.NT);
+        for (int c = 0; c < P.nchunks; ++c) {
+          const int ksteps = min(4, (P.Cin - c * 64 + 15) >> 4);
+          ptx::mbar_wait(&a_full[sa], pa);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_base = sA_u + uint32_t(sa) * P.a_stage_bytes;
+          for (int j = 0; j < P.bst_per_chunk; ++j) {
+            ptx::mbar_wait(&b_full[sb], pb);
+            ptx::tc_fence_after_sync();
+            const uint32_t b_base = sB_u + uint32_t(sb) * P.b_stage_bytes;
+            const int ntap = min(P.tps, P.taps - j * P.tps);
+            for (int tl = 0; tl < ntap; ++tl) {
+              const int tap = j * P.tps + tl;
+              const int r = tap / P.ks, s = tap - r * P.ks;
+              const uint32_t a_tap = a_base + uint32_t(r * P.WP + s) * 128u;
+              const uint32_t b_tap = b_base + uint32_t(tl) * P.NT * 128u;
+              for (int mb = 0; mb < P.NMB; ++mb) {
+                const uint32_t d = acc_col + uint32_t(mb * P.NT);
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint64_t da = ptx::umma_desc_sw128(a_tap + uint32_t(mb) * 16384u + uint32_t(k) * 32u, 1024);
+                  const uint64_t db = ptx::umma_desc_sw128(b_tap + uint32_t(k) * 32u, 1024);
+                  ptx::umma_bf16(d, da, db, idesc, (c | tap | k) != 0 ? 1u : 0u);
+                }
+              }
+            }
+            ptx::umma_commit(&b_empty[sb]);  // frees the weight stage once these MMAs retire
+            if (++sb == P.SB) { sb = 0; pb ^= 1; }
+          }
+          ptx::umma_commit(&a_empty[sa]);
+          if (++sa == P.SA) { sa = 0; pa ^= 1; }
+        }
+        ptx::umma_commit(&acc_full[as]);
+        if (++as == P.ACC) { as = 0; pacc ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ============================================================ epilogue
+    const int q = warp - 4;  // TMEM lane quarter
+    for (int i = tid - 128; i < P.NT; i += 128) s_bias[i] = 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    int as = 0, pacc = 0;
+    int cur_pass = -1;
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      const int t = work / P.npass, pass = work - t * P.npass;
+      int n, h0, w0;
+      decode_tile(P, t, n, h0, w0);
+      if (pass != cur_pass) {  // (re)load this pass's bias slice
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = tid - 128; i < P.NT; i += 128) s_bias[i] = P.bias[pass * P.NT + i];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_pass = pass;
+      }
+      ptx::mbar_wait(&acc_full[as], pacc);
+      ptx::tc_fence_after_sync();
+      const uint32_t acc_col = tmem_base + uint32_t(as * P.NMB * P.NT) + (uint32_t(q * 32) << 16);
+      const int cbase = pass * P.NT;  // first output channel of this pass
+      int xpar = 0;
+      for (int mb = 0; mb < P.NMB; ++mb) {
+        const int p = mb * 128 + q * 32 + lane;
+        const int hh = p / P.WP, ww = p - hh * P.WP;
+        const int h = h0 + hh, w = w0 + ww;
+        const bool valid = hh < P.TH && ww < P.TW && h < P.H && w < P.W;
+        for (int c0 = 0; c0 < P.NT; c0 += 16) {
+          uint32_t raw[16];
+          ptx::tmem_ld16(acc_col + uint32_t(mb * P.NT + c0), raw);
+          ptx::tmem_wait_ld();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float f = __uint_as_float(raw[j]) + s_bias[c0 + j];
+            if (P.relu) f = fmaxf(f, 0.f);
+            v[j] = f;
+          }
+          const int cg = cbase + c0;  // global output channel of v[0]
+          if (P.pool) {
+            // 2x2 max-pool: horizontal partner = lane^1, vertical partner = lane + WP inside this M-block
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+            const int rows_per_warp_shift = (P.WP == 64) ? 1 : 0;  // WP=64: warps (0,1)=row0,(2,3)=row1; WP=32: warp=row
+            const bool upper = rows_per_warp_shift ? (q >= 2) : (q & 1);
+            const int pair = rows_per_warp_shift ? (q & 1) : (q >> 1);
+            float* xb = s_xbuf + (xpar * 2 + pair) * (32 * 16);
+            if (upper) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) xb[j * 32 + lane] = v[j];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (!upper && valid && !(lane & 1) && cg < P.Cout) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], xb[j * 32 + lane]);
+              bf16* o = P.out + ((size_t(n) * (P.H >> 1) + (h >> 1)) * (P.W >> 1) + (w >> 1)) * P.out_ld + cg;
+              uint4 u0, u1;
+              u0.x = pack_bf16x2(v[0], v[1]); u0.y = pack_bf16x2(v[2], v[3]);
+              u0.z = pack_bf16x2(v[4], v[5]); u0.w = pack_bf16x2(v[6], v[7]);
+              u1.x = pack_bf16x2(v[8], v[9]); u1.y = pack_bf16x2(v[10], v[11]);
+              u1.z = pack_bf16x2(v[12], v[13]); u1.w = pack_bf16x2(v[14], v[15]);
+              *reinterpret_cast<uint4*>(o) = u0;
+              *reinterpret_cast<uint4*>(o + 8) = u1;
+            }
+            xpar ^= 1;
+          } else if (P.out_nchw) {
+            if (valid) {
+              for (int j = 0; j < 16 && cg + j < P.Cout; ++j) {
+                float f = v[j];
+                if (P.sigmoid) f = 1.0f / (1.0f + __expf(-f));
+                P.out_nchw[((size_t(n) * P.Cout + cg + j) * P.H + h) * P.W + w] = f;
+              }
+            }
+          } else if (valid && cg < P.Cout) {
+            bf16* o = P.out + ((size_t(n) * P.H + h) * P.W + w) * P.out_ld + cg;
+            if (cg + 16 <= P.Cout) {
+              uint4 u0, u1;
+              u0.x = pack_bf16x2(v[0], v[1]); u0.y = pack_bf16x2(v[2], v[3]);
+              u0.z = pack_bf16x2(v[4], v[5]); u0.w = pack_bf16x2(v[6], v[7]);
+              u1.x = pack_bf16x2(v[8], v[9]); u1.y = pack_bf16x2(v[10], v[11]);
+              u1.z = pack_bf16x2(v[12], v[13]); u1.w = pack_bf16x2(v[14], v[15]);
+              *reinterpret_cast<uint4*>(o) = u0;
+              *reinterpret_cast<uint4*>(o + 8) = u1;
+            } else {
+              for (int j = 0; j < 16 && cg + j < P.Cout; ++j) o[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[as]);
+      if (++as == P.ACC) { as = 0; pacc ^= 1; }
+    }
+  } else if (warp >= 8) {
+    // ============================================================ A-tile builders (producer modes)
+    if (IN_MODE != kInTma) {
+      const int pw = warp - 8;
+      int sa = 0, pa = 0;
+      const int rows = P.TH + 2 * P.halo;
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int t = work / P.npass;
+        int n, h0, w0;
+        decode_tile(P, t, n, h0, w0);
+        for (int c = 0; c < P.nchunks; ++c) {
+          if (lane == 0) ptx::mbar_wait(&a_empty[sa], pa ^ 1);
+          __syncwarp();
+          uint8_t* dst = sA + size_t(sa) * P.a_stage_bytes;
+          if (IN_MODE == kInNchw3) {
+            // fp32 planar 3-channel network input -> one 16-channel group (3 real + 13 zero) per pixel
+            for (int rr = pw; rr < rows; rr += kProducerWarps) {
+              const int h = h0 - P.halo + rr;
+              const bool hv = h >= 0 && h < P.H;
+              for (int wi = lane; wi < P.WP; wi += 32) {
+                const int w = w0 - P.halo + wi;
+                float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+                if (hv && w >= 0 && w < P.W) {
+                  const size_t o = (size_t(n) * 3 * P.H + h) * P.W + w;
+                  const size_t plane = size_t(P.H) * P.W;
+                  x0 = P.in_nchw[o]; x1 = P.in_nchw[o + plane]; x2 = P.in_nchw[o + 2 * plane];
+                }
+                const uint32_t prow = uint32_t(rr * P.WP + wi);
+                uint4 u0 = make_uint4(pack_bf16x2(x0, x1), pack_bf16x2(x2, 0.f), 0u, 0u);
+                *reinterpret_cast<uint4*>(dst + ptx::sw128_offset(prow, 0)) = u0;
+                *reinterpret_cast<uint4*>(dst + ptx::sw128_offset(prow, 1)) = make_uint4(0u, 0u, 0u, 0u);
+              }
+            }
+          } else {
+            // NHWC bf16 + per-channel pre-activation; lane -> (pixel-in-group, 16-byte unit)
+            const int cch = min(64, P.Cin - c * 64);           // channels in this chunk
+            const int ksteps = (cch + 15) >> 4;
+            const int upp = ksteps <= 1 ? 2 : (ksteps == 2 ? 4 : 8);  // 16-byte units per pixel (power of two)
+            const int u = lane & (upp - 1), psub = lane / upp, ppi = 32 / upp;
+            const int ch0 = c * 64 + u * 8;
+            float sc[8], sh[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const bool cv = ch0 + j < P.Cin;
+              sc[j] = cv ? P.pre_s[ch0 + j] : 0.f;
+              sh[j] = cv ? P.pre_t[ch0 + j] : 0.f;
+            }
+            const bool unit_valid = ch0 < P.Cin;  // Cin is a multiple of 8 on this path
+            for (int rr = pw; rr < rows; rr += kProducerWarps) {
+              const int h = h0 - P.halo + rr;
+              const bool hv = h >= 0 && h < P.H;
+              const bf16* rowp = P.in + (size_t(n) * P.H + (hv ? h : 0)) * P.W * P.in_ld + ch0;
+              for (int wi = psub; wi < P.WP; wi += ppi) {
+                const int w = w0 - P.halo + wi;
+                uint4 outv = make_uint4(0u, 0u, 0u, 0u);
+                if (hv && unit_valid && w >= 0 && w < P.W) {
+                  const uint4 raw = *reinterpret_cast<const uint4*>(rowp + size_t(w) * P.in_ld);
+                  const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+                  uint32_t ow[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float lo = __uint_as_float(rw[i] << 16), hi = __uint_as_float(rw[i] & 0xffff0000u);
+                    ow[i] = pack_bf16x2(fmaxf(fmaf(lo, sc[2 * i], sh[2 * i]), 0.f),
+                                        fmaxf(fmaf(hi, sc[2 * i + 1], sh[2 * i + 1]), 0.f));
+                  }
+                  outv = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                }
+                *reinterpret_cast<uint4*>(dst + ptx::sw128_offset(uint32_t(rr * P.WP + wi), uint32_t(u))) = outv;
+              }
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&a_full[sa]);
+          if (++sa == P.SA) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    void* p = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+constexpr int kSmemLimit = 232448 - 1024;  // 227 KB opt-in maximum minus alignment slack
+
+int pick_nt(int Cout, int* npass) {
+  *npass = 1;
+  if (Cout <= 16) return 16;
+  if (Cout <= 32) return 32;
+  if (Cout <= 64) return 64;
+  if (Cout <= 128) return 128;
+  *npass = (Cout + 255) / 256;
+  return 256;
+}
+
+struct TileCfg {
+  int TH, TW, WP, NMB, ACC, SA, SB, tps, a_stage_bytes, b_stage_bytes, smem_bytes;
+};
+
+// Choose the tile geometry: minimise issued MMA rows (tiles * NMB * 128) subject to shared-memory capacity.
+bool choose_tiles(const ConvDesc& d, int NT, int in_mode, TileCfg* out) {
+  const int halo = d.ks / 2, taps = d.ks * d.ks;
+  const int nchunks = (d.Cin + 63) / 64;
+  TileCfg best{};
+  double best_cost = 1e300;
+  for (int NMB = 1; NMB * NT <= 512 && NMB <= 8; NMB *= 2) {
+    const int ACC = (2 * NMB * NT <= 512) ? 2 : 1;
+    std::vector<int> wps;
+    if (d.pool) {
+      wps = {32, 64};
+    } else {
+      for (int wp = 2 * halo + 2; wp <= std::min(256, d.W + 2 * halo + 6); wp += 2) wps.push_back(wp);
+      if (d.W + 2 * halo <= 256) wps.push_back(d.W + 2 * halo);
+    }
+    for (int WP : wps) {
+      int TW = WP - 2 * halo;
+      if (TW < 1) continue;
+      int TH = (NMB * 128) / WP;
+      if (TH < 1) continue;
+      if (d.pool && (TH & 1)) continue;
+      TH = std::min(TH, d.pool ? ((d.H + 1) & ~1) : d.H);
+      if (TH < 1) continue;
+      const int a_rows_alloc = NMB * 128 + 2 * halo * WP + 8;
+      const int a_stage = int(align_up(size_t(a_rows_alloc) * 128, 1024));
+      const int tps = NT <= 32 ? taps : (NT == 64 ? std::min(taps, 3) : 1);
+      const int b_stage = tps * NT * 128;
+      const int tail = 1024 + 256 * 4 + 2 * 2 * 32 * 16 * 4 + 64;
+      // pipeline depth: as many stages as fit, capped
+      int SA = (nchunks >= 2 || true) ? 2 : 1, SB = 4;
+      auto total = [&](int sa, int sb) { return sa * a_stage + sb * b_stage + tail; };
+      while (SB > 2 && total(SA, SB) > kSmemLimit) --SB;
+      if (total(SA, SB) > kSmemLimit) continue;
+      while (SA < 3 && total(SA + 1, SB) <= kSmemLimit && in_mode != kInTma) ++SA;
+      while (SB < kMaxSB && total(SA, SB + 1) <= kSmemLimit && SB < 6) ++SB;
+      const double tiles = double((d.W + TW - 1) / TW) * ((d.H + TH - 1) / TH);
+      // per-tile time model (cycles): tensor pipe vs L2->smem operand traffic, plus the epilogue when the
+      // accumulator is single-buffered (then it cannot overlap the next tile's MMAs)
+      const int ksteps_total = (d.Cin + 15) / 16;
+      const double mma_cyc = double(NMB) * taps * ksteps_total * std::max(16.0, NT / 2.0);
+      const double l2_bytes = double(nchunks) * (double(TH + 2 * halo) * WP * 128.0 + double(taps) * NT * 128.0);
+      const double epi_cyc = double(NMB) * (NT / 16.0) * 70.0 + 300.0;
+      const double cost = tiles * (std::max(mma_cyc, l2_bytes / 36.0) + (ACC == 1 ? epi_cyc : 0.15 * epi_cyc) + 200.0);
+      if (cost < best_cost) {
+        best_cost = cost;
+        best = TileCfg{TH, TW, WP, NMB, ACC, SA, SB, tps, a_stage, b_stage, total(SA, SB) + 1024};
+      }
+    }
+  }
+  if (best_cost >= 1e300) return false;
+  *out = best;
+  return true;
+}
+
+}  // namespace
+
+int umma_pack_create(const float* w, const float* bias, int Cin, int Cout, int CoutP, int ks, UmmaPack** out) {
+  *out = nullptr;
+  if (ks != 1 && ks != 3) return fail("umma_pack: ks must be 1 or 3");
+  UmmaPack* p = new UmmaPack();
+  p->Cin = Cin; p->Cout = Cout; p->ks = ks;
+  p->NT = pick_nt(Cout, &p->npass);
+  p->nchunks = (Cin + 63) / 64;
+  const int taps = ks * ks, NT = p->NT;
+  const size_t block = size_t(NT) * 128;
+  std::vector<uint8_t> img(size_t(p->npass) * p->nchunks * taps * block, 0);
+  std::vector<float> hb(size_t(p->npass) * NT, 0.f);
+  for (int pass = 0; pass < p->npass; ++pass)
+    for (int c = 0; c < p->nchunks; ++c)
+      for (int t = 0; t < taps; ++t) {
+        uint8_t* blk = img.data() + ((size_t(pass) * p->nchunks + c) * taps + t) * block;
+        for (int nn = 0; nn < NT; ++nn) {
+          const int co = pass * NT + nn;
+          if (co >= Cout) continue;
+          for (int k = 0; k < 64; ++k) {
+            const int ci = c * 64 + k;
+            if (ci >= Cin) continue;
+            const float val = w[(size_t(t) * Cin + ci) * CoutP + co];
+            const bf16 b = __float2bfloat16_rn(val);
+            std::memcpy(blk + ptx::sw128_offset(uint32_t(nn), uint32_t(k >> 3)) + (k & 7) * 2, &b, 2);
+          }
+        }
+      }
+  for (int co = 0; co < Cout; ++co) hb[co] = bias[co];
+  if (cudaMalloc(&p->d_w, img.size()) != cudaSuccess || cudaMalloc(&p->d_bias, hb.size() * 4) != cudaSuccess) {
+    umma_pack_destroy(p);
+    return fail("umma_pack: cudaMalloc failed");
+  }
+  if (cudaMemcpy(p->d_w, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(p->d_bias, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    umma_pack_destroy(p);
+    return fail("umma_pack: upload failed");
+  }
+  *out = p;
+  return 0;
+}
+
+void umma_pack_destroy(UmmaPack* p) {
+  if (!p) return;
+  if (p->d_w) cudaFree(p->d_w);
+  if (p->d_bias) cudaFree(p->d_bias);
+  delete p;
+}
+
+bool conv_umma_supported(const ConvDesc& d) {
+  if (d.ks != 1 && d.ks != 3) return false;
+  if (d.in_nchw) return d.Cin <= 16 && !d.pre_scale;  // 3-channel planar network input
+  if (d.Cin % 8 != 0 || d.in_ld % 8 != 0) return false;
+  if (d.out_nchw) return d.Cout <= 16;
+  if (d.out_ld % 8 != 0) return false;
+  if (d.pool && ((d.H | d.W) & 1)) return false;
+  return true;
+}
+
+int conv_umma_launch(const ConvDesc& d, const UmmaPack& pk, cudaStream_t stream) {
+  if (!conv_umma_supported(d)) return fail("conv_umma: unsupported convolution shape");
+  if (pk.Cin != d.Cin || pk.Cout != d.Cout || pk.ks != d.ks) return fail("conv_umma: weight pack does not match");
+  const int in_mode = d.in_nchw ? kInNchw3 : (d.pre_scale ? kInPro : kInTma);
+  TileCfg tc;
+  if (!choose_tiles(d, pk.NT, in_mode, &tc)) return fail("conv_umma: no tile configuration fits shared memory");
+
+  KParams P{};
+  P.N = d.N; P.H = d.H; P.W = d.W; P.Cin = d.Cin; P.in_ld = d.in_ld;
+  P.ks = d.ks; P.halo = d.ks / 2; P.taps = d.ks * d.ks;
+  P.TH = tc.TH; P.TW = tc.TW; P.WP = tc.WP; P.NMB = tc.NMB; P.NT = pk.NT;
+  P.tiles_x = ceil_div(d.W, tc.TW); P.tiles_y = ceil_div(d.H, tc.TH);
+  P.ntiles = d.N * P.tiles_x * P.tiles_y;
+  P.nchunks = pk.nchunks; P.npass = pk.npass; P.Cout = d.Cout;
+  P.SA = tc.SA; P.SB = tc.SB; P.ACC = tc.ACC;
+  P.a_stage_bytes = tc.a_stage_bytes; P.b_stage_bytes = tc.b_stage_bytes;
+  P.tps = tc.tps; P.bst_per_chunk = ceil_div(P.taps, tc.tps);
+  P.a_rows = (tc.TH + 2 * P.halo) * tc.WP;
+  P.relu = d.relu; P.pool = d.pool; P.sigmoid = d.sigmoid;
+  P.in = reinterpret_cast<const bf16*>(d.in); P.in_nchw = d.in_nchw;
+  P.pre_s = d.pre_scale; P.pre_t = d.pre_shift;
+  P.wpack = pk.d_w; P.bias = pk.d_bias;
+  P.out = reinterpret_cast<bf16*>(d.out); P.out_ld = d.out_ld; P.out_nchw = d.out_nchw;
+
+  CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof(tmap));
+  if (in_mode == kInTma) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return fail("conv_umma: cuTensorMapEncodeTiled is not available from the driver");
+    if (reinterpret_cast<uintptr_t>(d.in) % 16 != 0) return fail("conv_umma: input pointer must be 16-byte aligned");
+    cuuint64_t gdim[4] = {cuuint64_t(d.Cin), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.N)};
+    cuuint64_t gstr[3] = {cuuint64_t(d.in_ld) * 2, cuuint64_t(d.W) * d.in_ld * 2, cuuint64_t(d.H) * d.W * d.in_ld * 2};
+    cuuint32_t box[4] = {64, cuuint32_t(tc.WP), cuuint32_t(tc.TH + 2 * P.halo), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.in), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("conv_umma: cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = std::min(P.ntiles * P.npass, sms);
+  const int threads = in_mode == kInTma ? 256 : 512;
+  auto launch = [&](auto kern) -> int {
+    CDAN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc.smem_bytes));
+    kern<<<grid, threads, tc.smem_bytes, stream>>>(tmap, P);
+    CDAN_CUDA_OK(cudaGetLastError());
+    return 0;
+  };
+  if (in_mode == kInTma) return launch(conv_umma_kernel<kInTma>);
+  if (in_mode == kInPro) return launch(conv_umma_kernel<kInPro>);
+  return launch(conv_umma_kernel<kInNchw3>);
+}
+
+}  // namespace cdan

@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "../../include/cdan_b200.h"
+#include "conv_umma.cuh"
 
 namespace cdan {
 
@@ -93,6 +94,7 @@ int pack_conv(cdan_plan* p, ConvLayer& L, const float* w, const float* bias, int
   }
   CDAN_TRY(upload(p, hw, &L.d_w));
   CDAN_TRY(upload(p, hb, &L.d_bias));
+  if (p->dt == kBF16) CDAN_TRY(umma_pack_create(hw.data(), hb.data(), CinPhys, Cout, L.CoutP, ks, &L.umma));
   return 0;
 }
 
@@ -198,7 +200,10 @@ int load_cbam(cdan_plan* p, const HostDict& sd, int slot, const std::string& pre
 void free_weights(cdan_plan* p) {
   for (void* d : p->owned) cudaFree(d);
   p->owned.clear();
-  for (auto& L : p->conv) L = ConvLayer{};
+  for (auto& L : p->conv) {
+    umma_pack_destroy(L.umma);
+    L = ConvLayer{};
+  }
   p->loaded = false;
 }
 
@@ -258,7 +263,7 @@ int ensure_workspace(cdan_plan* p, int N, int H, int W) {
 }
 
 // ------------------------------------------------------------------------------------------ schedule
-int conv_dispatch(cdan_plan* p, const ConvDesc& d, cudaStream_t s);  // below
+int conv_dispatch(cdan_plan* p, const ConvLayer& L, const ConvDesc& d, cudaStream_t s);  // below
 
 int run_conv(cdan_plan* p, ConvId id, int N, int H, int W, const void* in, int in_ld, void* out, int out_ld,
              int pool, cudaStream_t s, const float* in_nchw = nullptr, float* out_nchw = nullptr, int sigmoid = 0) {
@@ -271,12 +276,14 @@ int run_conv(cdan_plan* p, ConvId id, int N, int H, int W, const void* in, int i
   d.w = L.d_w; d.CoutP = L.CoutP; d.bias = L.d_bias;
   d.relu = L.relu; d.pool = pool;
   d.out = out; d.out_ld = out_ld; d.out_nchw = out_nchw; d.sigmoid = sigmoid;
-  CDAN_TRY(conv_dispatch(p, d, s));
+  CDAN_TRY(conv_dispatch(p, L, d, s));
   p->launches += 1;
   return 0;
 }
 
-int conv_dispatch(cdan_plan* p, const ConvDesc& d, cudaStream_t s) {
+// bf16 plans run every convolution on the tcgen05 kernel; fp32 plans (and conv_impl=1) use the CUDA-core kernel.
+int conv_dispatch(cdan_plan* p, const ConvLayer& L, const ConvDesc& d, cudaStream_t s) {
+  if (p->dt == kBF16 && p->conv_impl == 0 && L.umma && conv_umma_supported(d)) return conv_umma_launch(d, *L.umma, s);
   return conv_simt_launch(d, p->dt, s);
 }
 
