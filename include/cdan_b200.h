@@ -50,7 +50,8 @@ CDAN_API int cdan_plan_destroy(cdan_plan* plan);
 CDAN_API int cdan_plan_load_weights(cdan_plan* plan, int n, const char* const* keys, const void* const* ptrs,
                            const int64_t* numels);
 
-/* Options: "conv_impl" = 0 auto (tcgen05 where supported), 1 force CUDA-core path. */
+/* Options: "conv_impl" = 0 auto (tcgen05 where supported), 1 force CUDA-core path;
+ *          "profile"   = 1 brackets every launch group with CUDA events on the launching stream. */
 CDAN_API int cdan_plan_set_option(cdan_plan* plan, const char* name, int value);
 
 /* Bytes of workspace the plan will hold for an [N,3,H,W] forward (H and W must be multiples of 8). */
@@ -70,6 +71,10 @@ CDAN_API int cdan_stage_read(cdan_plan* plan, void* stream, const char* name, fl
 
 /* Number of kernels launched by the most recent cdan_forward on this plan. */
 CDAN_API int cdan_last_launch_count(cdan_plan* plan);
+
+/* With option "profile"=1: drain the recorded spans into text lines "label total_ms count\n" (labels:
+ * "conv|<state_dict prefix>|<umma_tma|umma_pro|simt>", "cbam|C<channels>", "glue|up_add") and reset. Synchronises. */
+CDAN_API int cdan_profile_read(cdan_plan* plan, char* buf, size_t buflen);
 
 /* ---- single operators (unit tests; all tensors fp32 NCHW on the device, converted internally to the dtype's
  *      NHWC layout).  impl: 0 auto, 1 CUDA-core, 2 tcgen05. */

@@ -33,6 +33,7 @@ _PROTOTYPES = {
     "cdan_forward_host": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
     "cdan_stage_read": (_c_int, [_c_void_p, _c_void_p, _c_char_p, _c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "cdan_last_launch_count": (_c_int, [_c_void_p]),
+    "cdan_profile_read": (_c_int, [_c_void_p, ctypes.c_char_p, ctypes.c_size_t]),
     "cdan_op_conv2d": (_c_int, [_c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p,
                                 _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
     "cdan_op_cbam": (_c_int, [_c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
@@ -162,6 +163,16 @@ class Plan:
         _check(lib().cdan_stage_read(self._h, s, name.encode(), None, shape), "stage_read")
         out = torch.empty(tuple(shape), dtype=torch.float32, device=self.device)
         _check(lib().cdan_stage_read(self._h, s, name.encode(), _ptr(out), shape), "stage_read")
+        return out
+
+    def profile_read(self) -> Dict[str, Tuple[float, int]]:
+        """Drain the per-launch CUDA-event spans recorded since the last call (needs set_option('profile', 1))."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        _check(lib().cdan_profile_read(self._h, buf, len(buf)), "profile_read")
+        out: Dict[str, Tuple[float, int]] = {}
+        for line in buf.value.decode().splitlines():
+            label, ms, cnt = line.rsplit(" ", 2)
+            out[label] = (float(ms), int(cnt))
         return out
 
     @property

@@ -262,6 +262,32 @@ int ensure_workspace(cdan_plan* p, int N, int H, int W) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ profiling spans
+cudaEvent_t get_event(cdan_plan* p) {
+  if (!p->event_pool.empty()) {
+    cudaEvent_t e = p->event_pool.back();
+    p->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+struct SpanGuard {  // records a pair of events around the launches issued in its scope
+  cdan_plan* p;
+  cudaStream_t s;
+  size_t idx = size_t(-1);
+  SpanGuard(cdan_plan* plan, cudaStream_t stream, const std::string& label) : p(plan), s(stream) {
+    if (!p->profile) return;
+    p->spans.push_back({label, get_event(p), get_event(p)});
+    idx = p->spans.size() - 1;
+    cudaEventRecord(p->spans[idx].e0, s);
+  }
+  ~SpanGuard() {
+    if (idx != size_t(-1)) cudaEventRecord(p->spans[idx].e1, s);
+  }
+};
+
 // ------------------------------------------------------------------------------------------ schedule
 int conv_dispatch(cdan_plan* p, const ConvLayer& L, const ConvDesc& d, cudaStream_t s);  // below
 
@@ -276,6 +302,8 @@ int run_conv(cdan_plan* p, ConvId id, int N, int H, int W, const void* in, int i
   d.w = L.d_w; d.CoutP = L.CoutP; d.bias = L.d_bias;
   d.relu = L.relu; d.pool = pool;
   d.out = out; d.out_ld = out_ld; d.out_nchw = out_nchw; d.sigmoid = sigmoid;
+  const bool umma = p->dt == kBF16 && p->conv_impl == 0 && L.umma && conv_umma_supported(d);
+  SpanGuard span(p, s, std::string("conv|") + L.name + (umma ? (d.pre_scale || d.in_nchw ? "|umma_pro" : "|umma_tma") : "|simt"));
   CDAN_TRY(conv_dispatch(p, L, d, s));
   p->launches += 1;
   return 0;
@@ -302,6 +330,7 @@ int run_cbam(cdan_plan* p, int slot, const void* x, const void* mul, void* out, 
   const CbamLayer& L = p->cbam[slot];
   CbamScratch sc;
   cbam_scratch_carve(p->buf.cbam_scratch, N, L.C, h, w, &sc);
+  SpanGuard span(p, s, "cbam|C" + std::to_string(L.C));
   CDAN_TRY(cbam_launch(p->dt, x, L.C, mul, L.C, out, L.C, N, h, w, L.C, L.w, sc, s));
   p->launches += 5;
   return 0;
@@ -333,16 +362,16 @@ int forward_impl(cdan_plan* p, cudaStream_t s, const float* x, float* y, int N, 
   CDAN_TRY(run_cbam(p, 0, b.E4, nullptr, b.B0, N, H8, W8, s));
   // ---- Decoder (models/cdan.py:126-159)
   CDAN_TRY(run_conv(p, DEC1, N, H8, W8, b.B0, 512, b.T1, 256, 0, s));
-  CDAN_TRY(up_add_launch(dt, b.T1, 256, b.D3, 320, b.A1, 256, N, H8, W8, 256, 0, s));
+  { SpanGuard span(p, s, "glue|up_add"); CDAN_TRY(up_add_launch(dt, b.T1, 256, b.D3, 320, b.A1, 256, N, H8, W8, 256, 0, s)); }
   CDAN_TRY(run_cbam(p, 1, b.A1, b.DN3, b.C1, N, H8, W8, s));
   CDAN_TRY(run_conv(p, DEC2, N, H8, W8, b.C1, 256, b.T2, 128, 0, s));
-  CDAN_TRY(up_add_launch(dt, b.T2, 128, b.D2, 192, b.U2, 128, N, H4, W4, 128, 1, s));
+  { SpanGuard span(p, s, "glue|up_add"); CDAN_TRY(up_add_launch(dt, b.T2, 128, b.D2, 192, b.U2, 128, N, H4, W4, 128, 1, s)); }
   CDAN_TRY(run_cbam(p, 2, b.U2, b.DN2, b.C2, N, H4, W4, s));
   CDAN_TRY(run_conv(p, DEC3, N, H4, W4, b.C2, 128, b.T3, 64, 0, s));
-  CDAN_TRY(up_add_launch(dt, b.T3, 64, b.D1, 128, b.U3, 64, N, H2, W2, 64, 1, s));
+  { SpanGuard span(p, s, "glue|up_add"); CDAN_TRY(up_add_launch(dt, b.T3, 64, b.D1, 128, b.U3, 64, N, H2, W2, 64, 1, s)); }
   CDAN_TRY(run_cbam(p, 3, b.U3, b.DN1, b.C3, N, H2, W2, s));
   CDAN_TRY(run_conv(p, DEC4, N, H2, W2, b.C3, 64, b.T4, 8, 0, s));
-  CDAN_TRY(up_add_input_launch(dt, b.T4, 8, x, b.FD, 80, 16, N, H, W, s));
+  { SpanGuard span(p, s, "glue|up_add"); CDAN_TRY(up_add_input_launch(dt, b.T4, 8, x, b.FD, 80, 16, N, H, W, s)); }
   p->launches += 4;
   // final DenseBlock(3,3,16,4) + sigmoid, written straight to the caller's fp32 NCHW output
   CDAN_TRY(run_dense(p, FDL0, N, H, W, b.FD, 80, 16, nullptr, 3, s, y));
@@ -411,6 +440,10 @@ int cdan_plan_destroy(cdan_plan* p) {
 
 int cdan_plan_set_option(cdan_plan* p, const char* name, int value) {
   if (!p || !name) return fail("cdan_plan_set_option: NULL argument");
+  if (!strcmp(name, "profile")) {
+    p->profile = value ? 1 : 0;
+    return 0;
+  }
   if (!strcmp(name, "conv_impl")) {
     if (value < 0 || value > 1) return fail("conv_impl must be 0 (auto) or 1 (CUDA cores)");
     p->conv_impl = value;
@@ -497,5 +530,28 @@ int cdan_stage_read(cdan_plan* p, void* stream, const char* name, float* dst, in
 }
 
 int cdan_last_launch_count(cdan_plan* p) { return p ? p->launches : 0; }
+
+int cdan_profile_read(cdan_plan* p, char* buf, size_t buflen) {
+  if (!p || !buf || buflen == 0) return fail("cdan_profile_read: NULL argument");
+  DeviceGuard g(p->device);
+  std::map<std::string, std::pair<double, int>> acc;
+  std::vector<std::string> order;
+  for (auto& sp : p->spans) {
+    CDAN_CUDA_OK(cudaEventSynchronize(sp.e1));
+    float ms = 0.f;
+    CDAN_CUDA_OK(cudaEventElapsedTime(&ms, sp.e0, sp.e1));
+    if (!acc.count(sp.label)) order.push_back(sp.label);
+    acc[sp.label].first += ms;
+    acc[sp.label].second += 1;
+    p->event_pool.push_back(sp.e0);
+    p->event_pool.push_back(sp.e1);
+  }
+  p->spans.clear();
+  std::string out;
+  for (auto& k : order) out += k + " " + std::to_string(acc[k].first) + " " + std::to_string(acc[k].second) + "\n";
+  if (out.size() + 1 > buflen) return fail("cdan_profile_read: buffer too small");
+  std::memcpy(buf, out.c_str(), out.size() + 1);
+  return 0;
+}
 
 }  // extern "C"

@@ -71,4 +71,9 @@ struct cdan_plan {
   cdan::Buffers buf{};
   std::map<std::string, cdan::Stage> stages;
   cudaStream_t own_stream = nullptr;
+  // optional per-launch CUDA-event timing ("profile" option): label -> accumulated ms / count
+  int profile = 0;
+  struct Span { std::string label; cudaEvent_t e0, e1; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> event_pool;
 };
