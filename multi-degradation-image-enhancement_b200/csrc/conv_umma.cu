@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
   float* s_bias = reinterpret_cast<float*>(sTail);                // [NT]
   float* s_xbuf = s_bias + 256;                                   // pool exchange: [2][2 warps][32 lanes][32 cols]
 
-  __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], b_full[kMaxSB], b_empty[kMaxSB], acc_full[2], acc_empty[2];
+  __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], raw_full[kMaxSA], b_full[kMaxSB], b_empty[kMaxSB], acc_full[2],
+      acc_empty[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
     for (int i = 0; i < P.SA; ++i) {
       ptx::mbar_init(&a_full[i], IN_MODE == kInTma ? 1 : kProducerWarps);
       ptx::mbar_init(&a_empty[i], 1);
+      ptx::mbar_init(&raw_full[i], 1);
     }
     for (int i = 0; i < P.SB; ++i) {
       ptx::mbar_init(&b_full[i], 1);
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
       ptx::mbar_init(&acc_empty[i], 4);
     }
     ptx::fence_mbar_init();
-    if (IN_MODE == kInTma) ptx::prefetch_tmap(&tmapA);
+    if (IN_MODE != kInNchw3) ptx::prefetch_tmap(&tmapA);
   }
   if (warp == 2) {
     ptx::tmem_alloc(&tmem_base_s, 512);
@@ -126,18 +128,19 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
         int n, h0, w0;
         decode_tile(P, t, n, h0, w0);
         for (int c = 0; c < P.nchunks; ++c) {
-          if (IN_MODE == kInTma) {
-            ptx::mbar_wait(&a_empty[sa], pa ^ 1);
-            ptx::mbar_arrive_expect_tx(&a_full[sa], uint32_t(P.a_rows) * 128u);
-            ptx::tma_load_4d(sA + size_t(sa) * P.a_stage_bytes, &tmapA, c * 64, w0 - P.halo, h0 - P.halo, n,
-                             &a_full[sa]);
+          if (IN_MODE != kInNchw3) {
+            // TMA mode: the tile feeds the MMA directly; producer mode: it lands "raw" and warps 8-15 activate it
+            uint64_t* full = IN_MODE == kInTma ? &a_full[sa] : &raw_full[sa];
+            ptx::mbar_wait_relaxed(&a_empty[sa], pa ^ 1);
+            ptx::mbar_arrive_expect_tx(full, uint32_t(P.a_rows) * 128u);
+            ptx::tma_load_4d(sA + size_t(sa) * P.a_stage_bytes, &tmapA, c * 64, w0 - P.halo, h0 - P.halo, n, full);
             if (++sa == P.SA) { sa = 0; pa ^= 1; }
           }
           const uint8_t* wsrc = P.wpack + (size_t(pass) * P.nchunks + c) * P.taps * (size_t(P.NT) * 128);
           for (int j = 0; j < P.bst_per_chunk; ++j) {
             const int ntap = min(P.tps, P.taps - j * P.tps);
             const uint32_t bytes = uint32_t(ntap) * P.NT * 128u;
-            ptx::mbar_wait(&b_empty[sb], pb ^ 1);
+            ptx::mbar_wait_relaxed(&b_empty[sb], pb ^ 1);
             ptx::mbar_arrive_expect_tx(&b_full[sb], bytes);
             ptx::bulk_g2s(sB + size_t(sb) * P.b_stage_bytes, wsrc + size_t(j) * P.tps * P.NT * 128, bytes, &b_full[sb]);
             if (++sb == P.SB) { sb = 0; pb ^= 1; }
@@ -147,47 +150,56 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_bf16(128, P.NT);
-      const uint32_t sA_u = ptx::smem_u32(sA), sB_u = ptx::smem_u32(sB);
-      int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-        ptx::mbar_wait(&acc_empty[as], pacc ^ 1);
-        ptx::tc_fence_after_sync();
-        const uint32_t acc_col = tmem_base + uint32_t(as * P.NMB * P.NT);
-        for (int c = 0; c < P.nchunks; ++c) {
-          const int ksteps = min(4, (P.Cin - c * 64 + 15) >> 4);
-          ptx::mbar_wait(&a_full[sa], pa);
+    // The whole warp walks the pipeline (so the waits are convergent); one elected lane issues.  Descriptors are
+    // kept as {lo, hi} with a constant hi word, so each tcgen05.mma costs two 32-bit adds of issue overhead.
+    const uint32_t idesc = ptx::umma_idesc_bf16(128, P.NT);
+    const uint64_t desc_hi = ptx::umma_desc_sw128(0, 1024) & 0xffffffff00000000ull;
+    const uint32_t desc_lo_flags = uint32_t(ptx::umma_desc_sw128(0, 1024) & 0xffffffffull);  // LBO field
+    const uint32_t sA_u = ptx::smem_u32(sA), sB_u = ptx::smem_u32(sB);
+    int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      ptx::mbar_wait(&acc_empty[as], pacc ^ 1);
+      ptx::tc_fence_after_sync();
+      const uint32_t acc_col = tmem_base + uint32_t(as * P.NMB * P.NT);
+      for (int c = 0; c < P.nchunks; ++c) {
+        const int ksteps = min(4, (P.Cin - c * 64 + 15) >> 4);
+        ptx::mbar_wait(&a_full[sa], pa);
+        const uint32_t a_base = sA_u + uint32_t(sa) * P.a_stage_bytes;
+        for (int j = 0; j < P.bst_per_chunk; ++j) {
+          ptx::mbar_wait(&b_full[sb], pb);
           ptx::tc_fence_after_sync();
-          const uint32_t a_base = sA_u + uint32_t(sa) * P.a_stage_bytes;
-          for (int j = 0; j < P.bst_per_chunk; ++j) {
-            ptx::mbar_wait(&b_full[sb], pb);
-            ptx::tc_fence_after_sync();
-            const uint32_t b_base = sB_u + uint32_t(sb) * P.b_stage_bytes;
-            const int ntap = min(P.tps, P.taps - j * P.tps);
+          const uint32_t b_base = sB_u + uint32_t(sb) * P.b_stage_bytes;
+          const int ntap = min(P.tps, P.taps - j * P.tps);
+          if (ptx::elect_one()) {
             for (int tl = 0; tl < ntap; ++tl) {
               const int tap = j * P.tps + tl;
               const int r = tap / P.ks, s = tap - r * P.ks;
-              const uint32_t a_tap = a_base + uint32_t(r * P.WP + s) * 128u;
-              const uint32_t b_tap = b_base + uint32_t(tl) * P.NT * 128u;
+              // descriptor address fields are in 16-byte units: one pixel row = 8, one M-block = 1024, one K step = 2
+              uint32_t a_lo = desc_lo_flags | (((a_base + uint32_t(r * P.WP + s) * 128u) & 0x3FFFFu) >> 4);
+              const uint32_t b_lo = desc_lo_flags | (((b_base + uint32_t(tl) * P.NT * 128u) & 0x3FFFFu) >> 4);
+              const uint32_t first = (c | tap) != 0 ? 1u : 0u;
+              uint32_t d = acc_col;
               for (int mb = 0; mb < P.NMB; ++mb) {
-                const uint32_t d = acc_col + uint32_t(mb * P.NT);
-                for (int k = 0; k < ksteps; ++k) {
-                  const uint64_t da = ptx::umma_desc_sw128(a_tap + uint32_t(mb) * 16384u + uint32_t(k) * 32u, 1024);
-                  const uint64_t db = ptx::umma_desc_sw128(b_tap + uint32_t(k) * 32u, 1024);
-                  ptx::umma_bf16(d, da, db, idesc, (c | tap | k) != 0 ? 1u : 0u);
-                }
+                ptx::umma_bf16(d, desc_hi | a_lo, desc_hi | b_lo, idesc, first);
+                if (ksteps > 1) ptx::umma_bf16(d, desc_hi | (a_lo + 2), desc_hi | (b_lo + 2), idesc, 1u);
+                if (ksteps > 2) ptx::umma_bf16(d, desc_hi | (a_lo + 4), desc_hi | (b_lo + 4), idesc, 1u);
+                if (ksteps > 3) ptx::umma_bf16(d, desc_hi | (a_lo + 6), desc_hi | (b_lo + 6), idesc, 1u);
+                a_lo += 1024;
+                d += uint32_t(P.NT);
               }
             }
-            ptx::umma_commit(&b_empty[sb]);  // frees the weight stage once these MMAs retire
-            if (++sb == P.SB) { sb = 0; pb ^= 1; }
+            ptx::umma_commit(&b_empty[sb]);                        // frees the weight stage once these MMAs retire
+            if (j == P.bst_per_chunk - 1) {
+              ptx::umma_commit(&a_empty[sa]);                      // ... and the activation stage after its last tap
+              if (c == P.nchunks - 1) ptx::umma_commit(&acc_full[as]);
+            }
           }
-          ptx::umma_commit(&a_empty[sa]);
-          if (++sa == P.SA) { sa = 0; pa ^= 1; }
+          __syncwarp();
+          if (++sb == P.SB) { sb = 0; pb ^= 1; }
         }
-        ptx::umma_commit(&acc_full[as]);
-        if (++as == P.ACC) { as = 0; pacc ^= 1; }
+        if (++sa == P.SA) { sa = 0; pa ^= 1; }
       }
+      if (++as == P.ACC) { as = 0; pacc ^= 1; }
     }
   } else if (warp >= 4 && warp < 8) {
     // ============================================================ epilogue
@@ -206,7 +218,7 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
         asm volatile("bar.sync 1, 128;" ::: "memory");
         cur_pass = pass;
       }
-      ptx::mbar_wait(&acc_full[as], pacc);
+      ptx::mbar_wait_relaxed(&acc_full[as], pacc, 32);
       ptx::tc_fence_after_sync();
       const uint32_t acc_col = tmem_base + uint32_t(as * P.NMB * P.NT) + (uint32_t(q * 32) << 16);
       const int cbase = pass * P.NT;  // first output channel of this pass
@@ -288,39 +300,49 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
     if (IN_MODE != kInTma) {
       const int pw = warp - 8;
       int sa = 0, pa = 0;
-      const int rows = P.TH + 2 * P.halo;
       for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
         const int t = work / P.npass;
         int n, h0, w0;
         decode_tile(P, t, n, h0, w0);
         for (int c = 0; c < P.nchunks; ++c) {
-          if (lane == 0) ptx::mbar_wait(&a_empty[sa], pa ^ 1);
-          __syncwarp();
           uint8_t* dst = sA + size_t(sa) * P.a_stage_bytes;
           if (IN_MODE == kInNchw3) {
-            // fp32 planar 3-channel network input -> one 16-channel group (3 real + 13 zero) per pixel
-            for (int rr = pw; rr < rows; rr += kProducerWarps) {
-              const int h = h0 - P.halo + rr;
-              const bool hv = h >= 0 && h < P.H;
-              for (int wi = lane; wi < P.WP; wi += 32) {
-                const int w = w0 - P.halo + wi;
-                float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-                if (hv && w >= 0 && w < P.W) {
-                  const size_t o = (size_t(n) * 3 * P.H + h) * P.W + w;
-                  const size_t plane = size_t(P.H) * P.W;
-                  x0 = P.in_nchw[o]; x1 = P.in_nchw[o + plane]; x2 = P.in_nchw[o + 2 * plane];
+            // fp32 planar 3-channel network input -> one 16-channel group (3 real + 13 zero) per pixel.
+            // Loads of a whole batch of pixels are issued before any is consumed (memory-level parallelism).
+            ptx::mbar_wait_relaxed(&a_empty[sa], pa ^ 1);
+            const size_t plane = size_t(P.H) * P.W;
+            const float* img = P.in_nchw + size_t(n) * 3 * plane;
+            constexpr int U = 4;
+            for (int q0 = pw * 32 + lane; q0 < P.a_rows; q0 += kProducerWarps * 32 * U) {
+              float x[U][3];
+#pragma unroll
+              for (int i = 0; i < U; ++i) {
+                const int q = q0 + i * kProducerWarps * 32;
+                const int rr = q / P.WP, wi = q - rr * P.WP;
+                const int h = h0 - P.halo + rr, w = w0 - P.halo + wi;
+                const bool ok = q < P.a_rows && h >= 0 && h < P.H && w >= 0 && w < P.W;
+                const size_t o = ok ? size_t(h) * P.W + w : 0;
+                x[i][0] = ok ? img[o] : 0.f;
+                x[i][1] = ok ? img[o + plane] : 0.f;
+                x[i][2] = ok ? img[o + 2 * plane] : 0.f;
+              }
+#pragma unroll
+              for (int i = 0; i < U; ++i) {
+                const int q = q0 + i * kProducerWarps * 32;
+                if (q < P.a_rows) {
+                  *reinterpret_cast<uint4*>(dst + ptx::sw128_offset(uint32_t(q), 0)) =
+                      make_uint4(pack_bf16x2(x[i][0], x[i][1]), pack_bf16x2(x[i][2], 0.f), 0u, 0u);
+                  *reinterpret_cast<uint4*>(dst + ptx::sw128_offset(uint32_t(q), 1)) = make_uint4(0u, 0u, 0u, 0u);
                 }
-                const uint32_t prow = uint32_t(rr * P.WP + wi);
-                uint4 u0 = make_uint4(pack_bf16x2(x0, x1), pack_bf16x2(x2, 0.f), 0u, 0u);
-                *reinterpret_cast<uint4*>(dst + ptx::sw128_offset(prow, 0)) = u0;
-                *reinterpret_cast<uint4*>(dst + ptx::sw128_offset(prow, 1)) = make_uint4(0u, 0u, 0u, 0u);
               }
             }
           } else {
-            // NHWC bf16 + per-channel pre-activation; lane -> (pixel-in-group, 16-byte unit)
-            const int cch = min(64, P.Cin - c * 64);           // channels in this chunk
+            // The raw NHWC bf16 tile was delivered by TMA (zero outside the image / beyond Cin).  Apply the dense
+            // block pre-activation relu(s*x+t) IN PLACE in fp32; pixels outside the image stay zero, i.e. the conv
+            // padding is applied after the activation (reference models/cdan.py:41-46).
+            const int cch = min(64, P.Cin - c * 64);
             const int ksteps = (cch + 15) >> 4;
-            const int upp = ksteps <= 1 ? 2 : (ksteps == 2 ? 4 : 8);  // 16-byte units per pixel (power of two)
+            const int upp = ksteps <= 1 ? 2 : (ksteps == 2 ? 4 : 8);  // 16-byte units per pixel the MMA reads
             const int u = lane & (upp - 1), psub = lane / upp, ppi = 32 / upp;
             const int ch0 = c * 64 + u * 8;
             float sc[8], sh[8];
@@ -330,16 +352,17 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
               sc[j] = cv ? P.pre_s[ch0 + j] : 0.f;
               sh[j] = cv ? P.pre_t[ch0 + j] : 0.f;
             }
-            const bool unit_valid = ch0 < P.Cin;  // Cin is a multiple of 8 on this path
-            for (int rr = pw; rr < rows; rr += kProducerWarps) {
-              const int h = h0 - P.halo + rr;
-              const bool hv = h >= 0 && h < P.H;
-              const bf16* rowp = P.in + (size_t(n) * P.H + (hv ? h : 0)) * P.W * P.in_ld + ch0;
-              for (int wi = psub; wi < P.WP; wi += ppi) {
-                const int w = w0 - P.halo + wi;
-                uint4 outv = make_uint4(0u, 0u, 0u, 0u);
-                if (hv && unit_valid && w >= 0 && w < P.W) {
-                  const uint4 raw = *reinterpret_cast<const uint4*>(rowp + size_t(w) * P.in_ld);
+            const int step = kProducerWarps * ppi;
+            const int step_r = step / P.WP, step_w = step - step_r * P.WP;
+            int q = pw * ppi + psub;
+            int rr = q / P.WP, wi = q - rr * P.WP;
+            ptx::mbar_wait_relaxed(&raw_full[sa], pa);
+            if (ch0 < P.Cin) {
+              for (; q < P.a_rows; q += step) {
+                const int h = h0 - P.halo + rr, w = w0 - P.halo + wi;
+                if (h >= 0 && h < P.H && w >= 0 && w < P.W) {
+                  uint4* ptr = reinterpret_cast<uint4*>(dst + ptx::sw128_offset(uint32_t(q), uint32_t(u)));
+                  const uint4 raw = *ptr;
                   const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
                   uint32_t ow[4];
 #pragma unroll
@@ -348,9 +371,11 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
                     ow[i] = pack_bf16x2(fmaxf(fmaf(lo, sc[2 * i], sh[2 * i]), 0.f),
                                         fmaxf(fmaf(hi, sc[2 * i + 1], sh[2 * i + 1]), 0.f));
                   }
-                  outv = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                  *ptr = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 }
-                *reinterpret_cast<uint4*>(dst + ptx::sw128_offset(uint32_t(rr * P.WP + wi), uint32_t(u))) = outv;
+                wi += step_w;
+                rr += step_r;
+                if (wi >= P.WP) { wi -= P.WP; ++rr; }
               }
             }
           }
@@ -544,7 +569,7 @@ int conv_umma_launch(const ConvDesc& d, const UmmaPack& pk, cudaStream_t stream)
 
   CUtensorMap tmap;
   std::memset(&tmap, 0, sizeof(tmap));
-  if (in_mode == kInTma) {
+  if (in_mode != kInNchw3) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return fail("conv_umma: cuTensorMapEncodeTiled is not available from the driver");
     if (reinterpret_cast<uintptr_t>(d.in) % 16 != 0) return fail("conv_umma: input pointer must be 16-byte aligned");

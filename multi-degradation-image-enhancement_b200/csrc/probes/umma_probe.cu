@@ -152,6 +152,57 @@ __global__ void __launch_bounds__(128) k_probe_conv(const __grid_constant__ CUte
   if (warp == 0) ptx::tmem_dealloc(tmem, 32);
 }
 
+
+// ------------------------------------------------------------------------------------------------ T3
+// Issue-rate / throughput of back-to-back tcgen05.mma (M=128, K=16) for several N, one CTA per SM, operands fixed.
+__global__ void __launch_bounds__(128) k_probe_rate(int N, int reps, long long* cycles_out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;               // 4 M-blocks x 128 rows x 128 B = 64 KB
+  uint8_t* sB = smem + 65536;       // 256 rows x 128 B = 32 KB
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid / 32;
+  for (int i = tid; i < (65536 + 32768) / 16; i += 128) ((uint4*)smem)[i] = make_uint4(0, 0, 0, 0);
+  ptx::fence_proxy_async_smem();
+  if (tid == 0) { ptx::mbar_init(&bar, 1); ptx::fence_mbar_init(); }
+  if (warp == 0) { ptx::tmem_alloc(&tmem_base_s, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 1) {
+    long long t0 = 0, t1 = 0;
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, N);
+      const uint64_t hi = ptx::umma_desc_sw128(0, 1024) & 0xffffffff00000000ull;
+      const uint32_t fl = uint32_t(ptx::umma_desc_sw128(0, 1024));
+      const uint32_t a0 = fl | ((ptx::smem_u32(sA) & 0x3FFFF) >> 4), b0 = fl | ((ptx::smem_u32(sB) & 0x3FFFF) >> 4);
+      t0 = clock64();
+      for (int r = 0; r < reps; ++r) {
+        uint32_t a = a0 + uint32_t(r & 7) * 8;  // shifted views like the conv taps
+        uint32_t d = tmem;
+        for (int mb = 0; mb < 4; ++mb) {
+          ptx::umma_bf16(d, hi | a, hi | b0, idesc, 1u);
+          ptx::umma_bf16(d, hi | (a + 2), hi | (b0 + 2), idesc, 1u);
+          ptx::umma_bf16(d, hi | (a + 4), hi | (b0 + 4), idesc, 1u);
+          ptx::umma_bf16(d, hi | (a + 6), hi | (b0 + 6), idesc, 1u);
+          a += 1024;
+          d += (N < 128 ? N : 128) * (N <= 128 ? 1 : 0);
+        }
+      }
+      ptx::umma_commit(&bar);
+      ptx::mbar_wait(&bar, 0);
+      t1 = clock64();
+      cycles_out[blockIdx.x] = t1 - t0;
+    }
+    __syncwarp();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+}
+
 // ------------------------------------------------------------------------------------------------ host
 static float bf(bf16 v) { return __bfloat162float(v); }
 
@@ -298,6 +349,28 @@ int main() {
       printf("T2 h0=%d : tma_tile_mismatches=%d conv_max_abs_err=%.3e %s\n", h0, bad, maxerr,
              (bad == 0 && maxerr < 2e-3) ? "PASS" : "FAIL");
     }
+  }
+
+  // ---------------- T3
+  {
+    long long* dC;
+    CK(cudaMalloc(&dC, 148 * 8));
+    const int smem_bytes = 1024 + 65536 + 32768 + 1024;
+    CK(cudaFuncSetAttribute(k_probe_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    for (int N : {16, 32, 64, 128, 256}) {
+      const int reps = 500;  // 500 * 16 = 8000 MMAs
+      for (int it = 0; it < 2; ++it) {
+        k_probe_rate<<<148, 128, smem_bytes>>>(N, reps, dC);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("T3 N=%d CUDA ERROR %s\n", N, cudaGetErrorString(e)); return 7; }
+      }
+      std::vector<long long> c(148);
+      CK(cudaMemcpy(c.data(), dC, 148 * 8, cudaMemcpyDeviceToHost));
+      double avg = 0; for (auto v : c) avg += v; avg /= 148;
+      printf("T3 N=%3d : %.1f cycles per MMA (M=128,K=16), ideal %.1f -> %.1f%% of tensor peak\n", N, avg / (reps * 16.0),
+             N / 2.0, 100.0 * (N / 2.0) / (avg / (reps * 16.0)));
+    }
+    cudaFree(dC);
   }
   printf("probe done\n");
   return 0;

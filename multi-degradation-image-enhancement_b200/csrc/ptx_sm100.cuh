@@ -61,19 +61,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must fail loudly (trap -> launch failure), never hang the GPU.
-#ifndef CDAN_MBAR_TIMEOUT_CYCLES
-#define CDAN_MBAR_TIMEOUT_CYCLES (4000000000ll)
+// Bounded waits: a protocol bug must fail loudly (trap -> launch failure), never hang the GPU.
+// mbar_wait        : tight poll — for the latency-critical MMA issuer (one warp).
+// mbar_wait_relaxed: poll with nanosleep back-off — for producer / epilogue warps, so that their polling does not
+//                    steal issue slots from the warps doing real work on the same SM sub-partition.
+#ifndef CDAN_MBAR_MAX_POLLS
+#define CDAN_MBAR_MAX_POLLS (1u << 26)
 #endif
+__device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
+  printf("cdan_b200: mbarrier timeout block=(%d,%d) thread=%d smem=0x%x parity=%u\n", blockIdx.x, blockIdx.y,
+         threadIdx.x, smem_u32(bar), parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > CDAN_MBAR_TIMEOUT_CYCLES) {
-      printf("cdan_b200: mbarrier timeout block=(%d,%d) thread=%d smem=0x%x parity=%u\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
+    if (++polls > CDAN_MBAR_MAX_POLLS) mbar_timeout(bar, parity);
+  }
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns = 64) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(sleep_ns);
+    if (++polls > (CDAN_MBAR_MAX_POLLS >> 2)) mbar_timeout(bar, parity);
   }
 }
 

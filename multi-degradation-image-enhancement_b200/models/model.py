@@ -1,0 +1,183 @@
+"""`models.model.Model` — the caller of the hot path (reference models/model.py:25-363).
+
+`test_step` keeps the reference's behaviour (strict `load_state_dict`, `eval()`, `no_grad`, forward ->
+post-processing -> losses/metrics on raw and post-processed outputs -> PNG saving -> logger rows), but every tensor
+op on the per-batch path is a native sm_100a kernel: `self.network(inputs)` (CDAN plan), `apply_postprocessing`
+(fused post-processing kernels, no per-op host sync) and the PSNR/SSIM metrics (one fused reduction + one D2H per
+batch instead of one `.item()` per metric).  `train_step` is the reference's fp16-autocast training loop over the
+autograd composition of the same modules; it is outside the accelerated path (out of scope)."""
+from __future__ import annotations
+
+import os
+import shutil
+import time
+from typing import Dict
+
+import numpy as np
+import torch
+from PIL import Image
+from torch.optim import Adam
+
+from models.base import BaseModel
+from utils.loss_factory import build_loss_pipeline
+from utils.metrics_factory import build_metrics_pipeline
+from utils.postprocessing_factory import apply_postprocessing
+
+try:  # progress bars are cosmetic
+    from tqdm import tqdm
+except Exception:  # pragma: no cover
+    def tqdm(it, **_):
+        return it
+
+
+def _accumulate(sums: Dict[str, float], values: Dict[str, torch.Tensor]) -> None:
+    for k, v in values.items():
+        sums[k] = sums.get(k, 0.0) + float(v.item() if torch.is_tensor(v) else v)
+
+
+class Model(BaseModel):
+    def __init__(self, network, **kwargs):
+        super().__init__(**kwargs)
+        cfg = self.config
+        self.network = network.to(self.device)
+        self.optimizer = Adam(self.network.parameters(), lr=self.lr)
+        self.scaler = torch.amp.GradScaler("cuda", enabled=str(self.device).startswith("cuda"))
+        self.loss_cfg = cfg.get("loss", {}) or {}
+        self.metrics_cfg = cfg.get("metrics", {"enabled": False}) or {"enabled": False}
+        self.loss_pipe = build_loss_pipeline(self.loss_cfg, device=self.device)
+        self.metrics_pipe = build_metrics_pipeline(self.metrics_cfg, device=self.device)
+        self.postproc_cfg = cfg.get("post_processing", {"enabled": False}) or {"enabled": False}
+        save = dict(cfg.get("save_outputs", {}) or {})
+        save.setdefault("output_dir", self.output_images_path)
+        save.setdefault("save_raw", False)
+        save.setdefault("save_postprocessed", True)
+        save.setdefault("raw_prefix", "raw_")
+        save.setdefault("post_prefix", save.get("prefix", "output_"))
+        self.save_cfg = save
+        ev = cfg.get("evaluation", {}) or {}
+        self.eval_on_raw = bool(ev.get("raw", True))
+        self.eval_on_post = bool(ev.get("postprocessed", bool(self.postproc_cfg.get("enabled", False))))
+        log = cfg.get("logging", {}) or {}
+        self.logging_enabled = bool(log.get("enabled", False))
+        self.train_log_every = int((log.get("train", {}) or {}).get("log_every_n_batches", 0) or 0)
+        ck = log.get("checkpoints", {}) or {}
+        self.ckpt_enabled, self.ckpt_every = bool(ck.get("enabled", False)), int(ck.get("every_n_epochs", 10))
+        self.best_loss = float("inf")
+
+    # ------------------------------------------------------------------------------------------------ outputs
+    def _save_batch_outputs(self, outputs: torch.Tensor, start_index: int, prefix: str):
+        """x255 -> clip -> uint8 -> PNG (reference models/model.py:70-91)."""
+        if not self.save_cfg.get("enabled", True):
+            return
+        out_dir = self.save_cfg.get("output_dir", "outputs/")
+        os.makedirs(out_dir, exist_ok=True)
+        fmt, resize_hw = self.save_cfg.get("format", "png"), self.save_cfg.get("resize_hw", None)
+        u8 = (outputs.detach() * 255).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().cpu().numpy()
+        for i, arr in enumerate(u8):
+            img = Image.fromarray(np.ascontiguousarray(arr))
+            if resize_hw is not None:
+                img = img.resize((int(resize_hw[1]), int(resize_hw[0])), Image.BILINEAR)
+            img.save(os.path.join(out_dir, f"{prefix}{start_index + i + 1}.{fmt}"))
+
+    def _run_dir(self):
+        return getattr(self.logger, "run_dir", lambda: None)() if self.logger is not None else None
+
+    # ------------------------------------------------------------------------------------------------ training
+    def train_step(self):
+        """Reference training loop (models/model.py:138-227): autocast forward, loss pipeline, GradScaler step,
+        best-loss checkpoint.  Runs the autograd (PyTorch) composition of the network; not accelerated here."""
+        self.network.to(self.device)
+        use_cuda = str(self.device).startswith("cuda")
+        for epoch in range(self.epoch):
+            t0 = time.time()
+            self.network.train()
+            total, comps, nb = 0.0, {}, 0
+            for inputs, targets in tqdm(self.dataloader, desc=f"Training... Epoch: {epoch + 1}/{self.epoch}"):
+                inputs, targets = inputs.to(self.device), targets.to(self.device)
+                self.optimizer.zero_grad()
+                with torch.autocast("cuda", enabled=use_cuda):
+                    outputs = self.network(inputs)
+                    loss_dict = self.loss_pipe(outputs, targets=targets, inputs=inputs, is_paired=True)
+                    loss = loss_dict["total"]
+                self.scaler.scale(loss).backward()
+                self.scaler.step(self.optimizer)
+                self.scaler.update()
+                total += float(loss.item())
+                _accumulate(comps, {k: v for k, v in loss_dict.items() if k != "total"})
+                nb += 1
+            avg = total / max(1, nb)
+            if avg < self.best_loss:
+                self.best_loss = avg
+                self.save_model(self.network)
+                run_dir = self._run_dir()
+                if self.logging_enabled and run_dir:
+                    try:
+                        shutil.copyfile(os.path.join(self.model_path, self.model_name), os.path.join(run_dir, "best.pt"))
+                    except OSError:
+                        pass
+            if self.logging_enabled and self.ckpt_enabled and self.ckpt_every > 0 and (epoch + 1) % self.ckpt_every == 0:
+                run_dir = self._run_dir()
+                if run_dir:
+                    os.makedirs(os.path.join(run_dir, "checkpoints"), exist_ok=True)
+                    torch.save(self.network.state_dict(), os.path.join(run_dir, "checkpoints", f"epoch_{epoch + 1:03d}.pt"))
+            if self.logging_enabled and self.logger is not None:
+                row = {"type": "train", "epoch": epoch + 1, "loss_total": avg, "best_loss": self.best_loss,
+                       "epoch_time_s": time.time() - t0}
+                row.update({f"loss_{k}": v / max(1, nb) for k, v in comps.items()})
+                self.logger.log_train(row)
+            print(f"Epoch {epoch + 1}/{self.epoch} | loss: {avg:.4f} | best: {self.best_loss:.4f}")
+
+    # ------------------------------------------------------------------------------------------------ testing
+    def test_step(self):
+        path = os.path.join(self.model_path, self.model_name)
+        self.network.load_state_dict(torch.load(path, map_location=self.device))
+        self.network.eval()
+        post_on = bool(self.postproc_cfg.get("enabled", False))
+        max_save = self.save_cfg.get("max_images", None)
+        sums = {"pre_loss": {}, "pre_metric": {}, "post_loss": {}, "post_metric": {}}
+        seen, n_batches = 0, 0
+        with torch.no_grad():
+            for batch in tqdm(self.dataloader, desc="Testing..."):
+                inputs, targets = (batch if self.is_dataset_paired else (batch, None))
+                inputs = inputs.to(self.device)
+                targets = None if targets is None else targets.to(self.device)
+                raw = self.network(inputs)                              # native CDAN forward
+                pp = apply_postprocessing(raw, self.postproc_cfg)       # native post-processing kernels
+                if self.is_dataset_paired:
+                    if self.eval_on_raw:
+                        _accumulate(sums["pre_loss"], self.loss_pipe(raw, targets=targets, inputs=inputs, is_paired=True))
+                        _accumulate(sums["pre_metric"], self.metrics_pipe(raw, targets=targets, inputs=inputs, is_paired=True))
+                    if self.eval_on_post and post_on:
+                        _accumulate(sums["post_loss"], self.loss_pipe(pp, targets=targets, inputs=inputs, is_paired=True))
+                        _accumulate(sums["post_metric"], self.metrics_pipe(pp, targets=targets, inputs=inputs, is_paired=True))
+                if self.save_cfg.get("enabled", True) and (max_save is None or seen < max_save):
+                    if self.save_cfg.get("save_raw", False):
+                        self._save_batch_outputs(raw, seen, self.save_cfg.get("raw_prefix", "raw_"))
+                    if self.save_cfg.get("save_postprocessed", True):
+                        self._save_batch_outputs(pp, seen, self.save_cfg.get("post_prefix", "output_"))
+                seen += raw.shape[0]
+                n_batches += 1
+                if max_save is not None and seen >= max_save:
+                    break
+        denom = max(1, n_batches)
+        avg = {k: {n: v / denom for n, v in d.items()} for k, d in sums.items()}
+        stages = []
+        if self.is_dataset_paired and self.eval_on_raw:
+            stages.append(("PRE", "pre"))
+        if self.is_dataset_paired and self.eval_on_post and post_on:
+            stages.append(("POST", "post"))
+        for label, key in stages:
+            print(f"[{label}] Losses -> " + ", ".join(f"{k}: {v:.4f}" for k, v in avg[key + "_loss"].items()))
+            if avg[key + "_metric"]:
+                print(f"[{label}] Metrics -> " + ", ".join(f"{k}: {v:.4f}" for k, v in avg[key + "_metric"].items()))
+        if self.logging_enabled and self.logger is not None:
+            for _, key in stages:
+                row = {"type": "test", "stage": key, "batches": n_batches}
+                row.update({f"loss_{k}": float(v) for k, v in avg[key + "_loss"].items()})
+                row.update({f"metric_{k}": float(v) for k, v in avg[key + "_metric"].items()})
+                self.logger.log_test(row)
+            if not self.is_dataset_paired:
+                self.logger.log_test({"type": "test", "stage": "unpaired", "batches": n_batches})
+            self.logger.set_summary({"best_train_loss": float(self.best_loss), "test_batches": n_batches,
+                                     "post_processing_enabled": post_on})
+        self.last_test_averages = avg
