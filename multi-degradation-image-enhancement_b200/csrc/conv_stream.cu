@@ -1,0 +1,783 @@
+// Streaming tcgen05 convolution for sm_100a: the kernel behind every narrow-output layer of CDAN (the 16 dense-block
+// 3x3 layers, the 4 transition 1x1 convs, decoder.conv4 and encoder.conv1) — reference models/cdan.py:8-53,70-98.
+//
+// Formulation.  A CTA walks a COLUMN STRIP of one image top to bottom.  One input row of the strip (128 pixels incl.
+// the horizontal halo, one 64-channel K-chunk = 16 KB, 128-byte-swizzled K-major) is one pipeline stage and one MMA
+// M-block: TMEM lane p <-> strip pixel p.  For a 3x3 convolution the three VERTICAL taps are folded into the MMA N
+// dimension: input row j is multiplied once by [W(r=2) | W(r=1) | W(r=0)] (N = 3*NT) and the three NT-column blocks
+// accumulate straight into the accumulators of output rows j-1, j, j+1, which sit in consecutive slots of a TMEM
+// RING.  The three horizontal taps are three A descriptors shifted by one pixel row (128 B) of the same stage.
+//   * N = 48 instead of 16 costs 44 instead of 39 cycles per tcgen05.mma (measured, profiles/r02_probe.log), so a
+//     16-channel dense layer issues 3x fewer, equally expensive MMAs: 20 % -> 55 % of the tensor pipe.
+//   * every activation row is loaded from HBM exactly once per strip (no vertical halo re-reads), stages are small
+//     (16 KB) so 8-12 of them are in flight per SM.
+//   * a finished accumulator row is read by the epilogue and immediately re-zeroed (tcgen05.st), so all MMAs use
+//     accumulate=1.  Ring wrap: input row G writes slots (G mod R)+{0,1,2}; slots R and R+1 are "shadow" copies of
+//     slots 0 and 1, summed by the epilogue — the N=3*NT window never has to be split.
+// encoder.conv1 (3 input channels, fp32 NCHW) additionally folds the three HORIZONTAL taps into K (k = s*3+ci, one
+// K=16 step), so a whole input row is ONE tcgen05.mma with N = 192, and its epilogue max-pools 2x2 (vertical pair =
+// two ring slots of the same thread, horizontal pair = lane^1).
+// 1x1 convolutions use the same pipeline with a window of one slot and fresh accumulators (no clearing).
+//
+// Warp roles: 0 TMA producer (+ resident weights), 1 MMA issuer, 2 TMEM allocator, 4-11 epilogue (two groups of four,
+// alternating accumulator rows), 12-19 A-stage workers (dense pre-activation relu(s*x+t) in place, or the conv1 row
+// builder).  All waits are bounded (ptx::mbar_wait traps), so a protocol bug fails loudly instead of hanging.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "conv_umma.cuh"
+#include "ptx_sm100.cuh"
+
+namespace cdan {
+
+struct StreamPack {
+  uint8_t* d_w = nullptr;   // fold / 1x1 image: [pass][chunk][s][NMMA rows][128 B swizzled]
+  uint8_t* d_wk = nullptr;  // conv1 K-folded image: [192 rows][128 B swizzled] (only when Cin == 3, ks == 3, Cout <= 64)
+  float* d_bias = nullptr;  // [npass * NT]
+  int Cin = 0, Cout = 0, ks = 3, NT = 0, npass = 1, nchunks = 0;
+  size_t pass_bytes = 0;
+};
+
+namespace {
+
+enum SIn : int { kSTma = 0, kSPro = 1, kSNchw = 2 };
+enum SEpi : int { kSStore = 0, kSPool = 1, kSNchwOut = 2 };
+
+constexpr int kStage = 16384;  // one input row: 128 pixels x 64 channels bf16
+constexpr int kMaxSA = 12;
+// conv1 raw fp32 row ring: one stage = 3 channels x 136 pixels starting at column w0-4 (TMA needs the innermost start
+// coordinate 16-byte aligned; w0 is a multiple of 4), 2 KB per stage.
+constexpr int kRawStages = 8, kRawW = 136, kRawFloats = 512;
+constexpr int kMaxR = 32;
+// Warp layout: warps 0-3 control, 4-11 epilogue (two groups of four alternating accumulator rows), then the A-stage
+// workers (8 warps for the dense pre-activation, 4 for conv1's row builder, none for TMA-fed layers).
+constexpr int kEpiWarp0 = 4;
+__host__ __device__ constexpr int epi_warps(int) { return 8; }
+__host__ __device__ constexpr int work_warps(int in_mode) { return in_mode == 0 ? 0 : (in_mode == 1 ? 8 : 4); }
+
+struct SParams {
+  int N, H, W, Cin;
+  int pad;       // 1: 3x3, 0: 1x1
+  int NT, NMMA;  // output channels per accumulator row / MMA N
+  int SW;        // TMEM columns per ring slot (= NT, or 3*NT when the horizontal taps are folded into N as well)
+  int R;         // ring slots (excluding the two shadow slots)
+  int TW, strips, SEG, segs, nitems;
+  int nchunks, nS, SA;
+  int relu, sigmoid, Cout;
+  uint32_t wbytes;
+  const bf16* in;
+  int in_ld;
+  const float* in_nchw;
+  const float* pre_s;
+  const float* pre_t;
+  const uint8_t* wpack;
+  const float* bias;
+  bf16* out;
+  int out_ld;
+  float* out_nchw;
+};
+
+struct Item {
+  int n, w0, h0, h1;
+};
+__device__ __forceinline__ Item decode_item(const SParams& P, int item) {
+  const int per_img = P.strips * P.segs;
+  Item it;
+  it.n = item / per_img;
+  const int r = item - it.n * per_img;
+  const int seg = r / P.strips;
+  it.w0 = (r - seg * P.strips) * P.TW;
+  it.h0 = seg * P.SEG;
+  it.h1 = min(P.H, it.h0 + P.SEG);
+  return it;
+}
+
+__device__ __forceinline__ uint32_t bf2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bflo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bfhi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// Ring counter: index modulo `n` plus the number of wrap-arounds (mbarrier phase bookkeeping without integer division —
+// every role is a single warp running a dependent instruction stream, so per-row instruction count IS the row time).
+struct Ring {
+  int i = 0, w = 0;
+  __device__ __forceinline__ void step(int n) { if (++i == n) { i = 0; ++w; } }
+  __device__ __forceinline__ void add(int k, int n) { i += k; while (i >= n) { i -= n; ++w; } }  // small k
+  __device__ __forceinline__ void jump(int k, int n) { i += k; const int d = i / n; w += d; i -= d * n; }  // once per item
+};
+
+template <int IN, int FOLD, int EPI>
+__global__ void __launch_bounds__(640, 1) conv_stream_kernel(const __grid_constant__ CUtensorMap tmapA, const SParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sW = sA + size_t(P.SA) * kStage + 1024;
+  float* s_pre_s = reinterpret_cast<float*>(sW + P.wbytes);
+  float* s_pre_t = s_pre_s + P.nchunks * 64;
+  float* s_bias = s_pre_t + P.nchunks * 64;
+  float* s_raw = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_bias + max(P.NT, 64)) + 127) & ~uintptr_t(127));  // kSNchw only
+
+  __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], raw_full[kMaxSA], raw_empty[kRawStages], acc_done[kMaxR], acc_free[kMaxR], w_full;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int PAD = FOLD == 3 ? 1 : 0;
+  constexpr int kEpiWarps = epi_warps(IN), kWorkWarp0 = kEpiWarp0 + kEpiWarps, kWorkWarps = work_warps(IN);
+  constexpr int kEG = kEpiWarps / 4;  // epilogue groups
+  // SHIFT: all nine taps folded into N (N = 9*NT); lane l of warp-quarter q holds strip pixel 30*q + l - 1, the
+  // epilogue adds the three horizontal-tap column groups of lanes l-1, l, l+1 (valid outputs: l = 1..30).
+  constexpr bool SHIFT = FOLD == 3 && IN != kSNchw;
+
+  if (tid == 0) {
+    for (int i = 0; i < kMaxSA; ++i) {
+      ptx::mbar_init(&a_full[i], IN == kSTma ? 1 : kWorkWarps);
+      ptx::mbar_init(&a_empty[i], 1);
+      ptx::mbar_init(&raw_full[i], 1);
+      if (i < kRawStages) ptx::mbar_init(&raw_empty[i], 4);
+    }
+    for (int i = 0; i < P.R; ++i) {
+      ptx::mbar_init(&acc_done[i], 1);
+      ptx::mbar_init(&acc_free[i], 4);
+    }
+    ptx::mbar_init(&w_full, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&tmapA);
+#ifdef CDAN_MBAR_DEBUG
+    if (blockIdx.x == 0)
+      printf("barriers: a_full=0x%x a_empty=0x%x raw_full=0x%x raw_empty=0x%x acc_done=0x%x acc_free=0x%x w_full=0x%x\n", ptx::smem_u32(a_full),
+             ptx::smem_u32(a_empty), ptx::smem_u32(raw_full), ptx::smem_u32(raw_empty), ptx::smem_u32(acc_done), ptx::smem_u32(acc_free), ptx::smem_u32(&w_full));
+#endif
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(&tmem_base_s, 512);
+    ptx::tmem_relinquish();
+  }
+  for (int i = tid; i < P.nchunks * 64; i += blockDim.x) {
+    const bool ok = IN == kSPro && i < P.Cin;
+    s_pre_s[i] = ok ? P.pre_s[i] : 0.f;
+    s_pre_t[i] = ok ? P.pre_t[i] : 0.f;
+  }
+  for (int i = tid; i < P.NT; i += blockDim.x) s_bias[i] = P.bias[i];
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  if (FOLD == 3 && warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {  // ring accumulators start at zero
+    const uint32_t lb = tmem_base + (uint32_t((warp & 3) * 32) << 16);
+    for (int c = 0; c < 512; c += 16) ptx::tmem_st16_zero(lb + c);
+    ptx::tmem_wait_st();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+
+  if (warp == 0) {
+    // ============================================================ producer (one thread): resident weights, A rows via TMA
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(&w_full, P.wbytes);
+      for (uint32_t off = 0; off < P.wbytes; off += 32768)
+        ptx::bulk_g2s(sW + off, P.wpack + off, min(32768u, P.wbytes - off), &w_full);
+      if (IN == kSNchw) {
+        Ring rr;
+        for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+          const Item it = decode_item(P, item);
+          const int j0 = max(it.h0 - 1, 0), j1 = min(it.h1 + 1, P.H);
+          for (int j = j0; j < j1; ++j) {
+            ptx::mbar_wait(&raw_empty[rr.i], (rr.w & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx(&raw_full[rr.i], kRawW * 3 * 4);
+            ptx::tma_load_4d(s_raw + rr.i * kRawFloats, &tmapA, it.w0 - 4, j, 0, it.n, &raw_full[rr.i]);
+            rr.step(kRawStages);
+          }
+        }
+      } else {
+        Ring st;
+        for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+          const Item it = decode_item(P, item);
+          const int j0 = max(it.h0 - PAD, 0), j1 = min(it.h1 + PAD, P.H);
+          for (int j = j0; j < j1; ++j) {
+            for (int c = 0; c < P.nchunks; ++c) {
+              // kSTma: the row feeds the MMA directly; kSPro: it lands raw and the workers activate it in place
+              uint64_t* full = IN == kSTma ? &a_full[st.i] : &raw_full[st.i];
+              ptx::mbar_wait(&a_empty[st.i], (st.w & 1) ^ 1);
+              ptx::mbar_arrive_expect_tx(full, kStage);
+              uint8_t* dst = sA + size_t(st.i) * kStage;
+              if (SHIFT) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ptx::tma_load_4d(dst + q * 4096, &tmapA, c * 64, it.w0 - 1 + 30 * q, j, it.n, full);
+              } else {
+                ptx::tma_load_4d(dst, &tmapA, c * 64, it.w0, j, it.n, full);
+              }
+              st.step(P.SA);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, P.NMMA);
+      const uint64_t desc_hi = ptx::umma_desc_sw128(0, 1024) & 0xffffffff00000000ull;
+      const uint32_t flags = uint32_t(ptx::umma_desc_sw128(0, 1024) & 0xffffffffull);
+      const uint32_t a_base = flags | ((ptx::smem_u32(sA) & 0x3FFFFu) >> 4);
+      const uint32_t b_base = flags | ((ptx::smem_u32(sW) & 0x3FFFFu) >> 4);
+      const uint32_t blk16 = uint32_t(P.NMMA) * 8u;  // one [NMMA x 128 B] weight block in 16-byte units
+      const int klast = IN == kSNchw ? 1 : min(4, (P.Cin - (P.nchunks - 1) * 64 + 15) >> 4);
+      Ring st;   // A stage
+      Ring dr;   // accumulator row this input row's window starts at (G + jj)
+      Ring fr;   // newest accumulator row it touches (G + jj + 2*PAD): must have been drained R rows ago
+      fr.add(2 * PAD, P.R);
+      ptx::mbar_wait(&w_full, 0);
+      for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+        const Item it = decode_item(P, item);
+        const int n_in = it.h1 - it.h0 + 2 * PAD;
+        for (int jj = 0; jj < n_in; ++jj) {
+          const int j = it.h0 - PAD + jj;
+          if (fr.w > 0) ptx::mbar_wait(&acc_free[fr.i], (fr.w - 1) & 1);
+          ptx::tc_fence_after_sync();
+          if (j >= 0 && j < P.H) {
+            const uint32_t dcol = tmem_base + uint32_t(dr.i * P.SW);
+            uint32_t b0 = b_base;
+            for (int c = 0; c < P.nchunks; ++c) {
+              const int ksteps = c == P.nchunks - 1 ? klast : 4;
+              ptx::mbar_wait(&a_full[st.i], st.w & 1);
+              ptx::tc_fence_after_sync();
+              const uint32_t a0 = a_base + uint32_t(st.i) * (kStage >> 4);
+              const uint32_t acc0 = FOLD == 3 ? 1u : (c != 0 ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < (IN == kSNchw ? 1 : 4); ++k)
+                if (k < ksteps)
+                  ptx::umma_bf16(dcol, desc_hi | (a0 + uint32_t(2 * k)), desc_hi | (b0 + uint32_t(2 * k)), idesc, k == 0 ? acc0 : 1u);
+              ptx::umma_commit(&a_empty[st.i]);
+              st.step(P.SA);
+              b0 += blk16;
+            }
+          }
+          ptx::umma_commit(&acc_done[dr.i]);
+          dr.step(P.R);
+          fr.step(P.R);
+        }
+        if (PAD) {  // the two trailing accumulator rows of the segment receive no further input
+          ptx::umma_commit(&acc_done[dr.i]);
+          dr.step(P.R);
+          ptx::umma_commit(&acc_done[dr.i]);
+          dr.step(P.R);
+          fr.add(2, P.R);
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
+    // ============================================================ epilogue
+    const int eg = (warp - kEpiWarp0) >> 2, q = warp & 3;
+    const uint32_t lb = tmem_base + (uint32_t(q * 32) << 16);
+    const int px = q * 32 + lane;
+    Ring ar;  // first accumulator row of the current item
+    int apar = 0;  // parity of the running accumulator-row index A (rows alternate between the epilogue groups)
+    for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+      const Item it = decode_item(P, item);
+      const int n_acc = it.h1 - it.h0 + 4 * PAD;
+      const int col = SHIFT ? it.w0 - 1 + 30 * q + lane : it.w0 + px;
+      const bool col_ok = SHIFT ? (lane >= 1 && lane <= 30 && col < P.W && col < it.w0 + P.TW) : (px < P.TW && col < P.W);
+      if (EPI != kSPool) {
+        const int ii0 = kEG == 2 ? (eg ^ (apar & 1)) : 0;
+        Ring sr = ar;
+        sr.add(ii0, P.R);
+        int i = it.h0 - 2 * PAD + ii0;
+        // output address of (n, i, col): advanced by kEG rows per step
+        const size_t row_elems = EPI == kSNchwOut ? size_t(P.W) : size_t(P.W) * P.out_ld;
+        bf16* o_b = nullptr;
+        float* o_f = nullptr;
+        if (EPI == kSNchwOut) o_f = P.out_nchw + (size_t(it.n) * P.Cout * P.H + i) * P.W + col;
+        else o_b = P.out + ((size_t(it.n) * P.H + i) * P.W + col) * P.out_ld;
+        for (int ii = ii0; ii < n_acc; ii += kEG) {
+          const int slot = sr.i;
+          ptx::mbar_wait(&acc_done[slot], sr.w & 1);
+          ptx::tc_fence_after_sync();
+          const bool row_ok = i >= it.h0 && i < it.h1;
+          const bool shadow = FOLD == 3 && slot < 2;
+          const uint32_t tm = lb + uint32_t(slot * P.SW), ts = lb + uint32_t((P.R + slot) * P.SW);
+          // 8 output channels at a time keeps the live register set small (spills are L2 round trips here: with
+          // ~224 KB of shared memory in use the L1 has almost no capacity left)
+          for (int c0 = 0; c0 < P.NT; c0 += 8) {
+            uint32_t v[8];
+            if (SHIFT) {
+              // slot = [tap s=0 | s=1 | s=2] x 16 channels; out(l) = Y0(l-1) + Y1(l) + Y2(l+1)
+              uint32_t y0[8], y2[8];
+              if (row_ok) {
+                ptx::tmem_ld8(tm + c0, y0);
+                ptx::tmem_ld8(tm + 16 + c0, v);
+                ptx::tmem_ld8(tm + 32 + c0, y2);
+                if (shadow) {
+                  uint32_t w0[8], w1[8], w2[8];
+                  ptx::tmem_ld8(ts + c0, w0);
+                  ptx::tmem_ld8(ts + 16 + c0, w1);
+                  ptx::tmem_ld8(ts + 32 + c0, w2);
+                  ptx::tmem_wait_ld();
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    y0[e] = __float_as_uint(__uint_as_float(y0[e]) + __uint_as_float(w0[e]));
+                    v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(w1[e]));
+                    y2[e] = __float_as_uint(__uint_as_float(y2[e]) + __uint_as_float(w2[e]));
+                  }
+                } else {
+                  ptx::tmem_wait_ld();
+                }
+              }
+              ptx::tmem_st8_zero(tm + c0); ptx::tmem_st8_zero(tm + 16 + c0); ptx::tmem_st8_zero(tm + 32 + c0);
+              if (shadow) { ptx::tmem_st8_zero(ts + c0); ptx::tmem_st8_zero(ts + 16 + c0); ptx::tmem_st8_zero(ts + 32 + c0); }
+              if (row_ok) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float a0 = __shfl_up_sync(0xffffffffu, __uint_as_float(y0[e]), 1);
+                  const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(y2[e]), 1);
+                  v[e] = __float_as_uint(a0 + __uint_as_float(v[e]) + a2);
+                }
+              }
+            } else {
+              if (row_ok) {
+                ptx::tmem_ld8(tm + c0, v);
+                if (shadow) {
+                  uint32_t v2[8];
+                  ptx::tmem_ld8(ts + c0, v2);
+                  ptx::tmem_wait_ld();
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(v2[e]));
+                } else {
+                  ptx::tmem_wait_ld();
+                }
+              }
+              if (FOLD == 3) {
+                ptx::tmem_st8_zero(tm + c0);
+                if (shadow) ptx::tmem_st8_zero(ts + c0);
+              }
+            }
+            if (row_ok) {
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0), b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 4);
+              float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y, __uint_as_float(v[2]) + b0.z,
+                            __uint_as_float(v[3]) + b0.w, __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
+                            __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
+              if (P.relu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+              }
+              if (col_ok) {
+                if (EPI == kSNchwOut) {
+                  const size_t plane = size_t(P.H) * P.W;
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    if (c0 + e < P.Cout) o_f[size_t(c0 + e) * plane] = P.sigmoid ? 1.0f / (1.0f + __expf(-f[e])) : f[e];
+                } else if (c0 < P.Cout) {  // channel slices are padded to multiples of 8
+                  *reinterpret_cast<uint4*>(o_b + c0) = make_uint4(bf2(f[0], f[1]), bf2(f[2], f[3]), bf2(f[4], f[5]), bf2(f[6], f[7]));
+                }
+              }
+            }
+          }
+          if (FOLD == 3) ptx::tmem_wait_st();
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&acc_free[slot]);
+          sr.add(kEG, P.R);
+          i += kEG;
+          if (EPI == kSNchwOut) o_f += kEG * row_elems; else o_b += kEG * row_elems;
+        }
+      } else {
+        // 2x2 max-pool: accumulator rows (a, a+1) <-> image rows (i, i+1), i even; horizontal partner = lane ^ 1.
+        // Row pairs alternate between the two epilogue groups.  (A is even at every item start: segments are even.)
+        const int pp0 = kEG == 2 ? (eg ^ (apar >> 1)) : 0;  // first pair index of this group
+        Ring sr = ar;
+        sr.add(2 * pp0, P.R);
+        int i = it.h0 - 2 * PAD + 2 * pp0;
+        for (int ii = 2 * pp0; ii < n_acc; ii += 2 * kEG) {
+          const int sl0 = sr.i, sl1 = sr.i + 1;  // R is even, so a pair never straddles the ring end
+          ptx::mbar_wait(&acc_done[sl0], sr.w & 1);
+          ptx::mbar_wait(&acc_done[sl1], sr.w & 1);
+          ptx::tc_fence_after_sync();
+          const bool row_ok = i >= it.h0 && i < it.h1;
+          const bool sh0 = sl0 < 2, sh1 = sl1 < 2;
+          const uint32_t t0 = lb + uint32_t(sl0 * P.NT), t1 = lb + uint32_t(sl1 * P.NT);
+          const uint32_t ts0 = lb + uint32_t((P.R + sl0) * P.NT), ts1 = lb + uint32_t((P.R + sl1) * P.NT);
+          bf16* o_row = P.out + ((size_t(it.n) * (P.H >> 1) + (i >> 1)) * (P.W >> 1) + (col >> 1)) * P.out_ld;
+          for (int c0 = 0; c0 < P.NT; c0 += 16) {
+            uint32_t pk[4];  // this lane's 8 pooled channels of the 16-channel group, packed bf16
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int cc = c0 + 8 * hh;
+              uint32_t v0[8], v1[8];
+              if (row_ok) {
+                ptx::tmem_ld8(t0 + cc, v0);
+                ptx::tmem_ld8(t1 + cc, v1);
+                if (sh0 || sh1) {
+                  uint32_t w0[8], w1[8];
+                  if (sh0) ptx::tmem_ld8(ts0 + cc, w0);
+                  if (sh1) ptx::tmem_ld8(ts1 + cc, w1);
+                  ptx::tmem_wait_ld();
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    if (sh0) v0[e] = __float_as_uint(__uint_as_float(v0[e]) + __uint_as_float(w0[e]));
+                    if (sh1) v1[e] = __float_as_uint(__uint_as_float(v1[e]) + __uint_as_float(w1[e]));
+                  }
+                } else {
+                  ptx::tmem_wait_ld();
+                }
+              }
+              ptx::tmem_st8_zero(t0 + cc);
+              ptx::tmem_st8_zero(t1 + cc);
+              if (sh0) ptx::tmem_st8_zero(ts0 + cc);
+              if (sh1) ptx::tmem_st8_zero(ts1 + cc);
+              if (row_ok) {
+                const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cc), b1 = *reinterpret_cast<const float4*>(s_bias + cc + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float m[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  float x = fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e]));
+                  x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+                  x += bb[e];  // max commutes with the per-channel bias and with ReLU
+                  m[e] = P.relu ? fmaxf(x, 0.f) : x;
+                }
+                // even lane keeps channels [c0, c0+8), odd lane [c0+8, c0+16) of the pooled pixel
+                if ((lane & 1) == hh) {
+                  pk[0] = bf2(m[0], m[1]); pk[1] = bf2(m[2], m[3]); pk[2] = bf2(m[4], m[5]); pk[3] = bf2(m[6], m[7]);
+                }
+              }
+            }
+            if (row_ok) {
+              const int cg = c0 + ((lane & 1) ? 8 : 0);
+              if (col_ok && cg < P.Cout) *reinterpret_cast<uint4*>(o_row + cg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+          ptx::tmem_wait_st();
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::mbar_arrive(&acc_free[sl0]);
+            ptx::mbar_arrive(&acc_free[sl1]);
+          }
+          sr.add(2 * kEG, P.R);
+          i += 2 * kEG;
+        }
+      }
+      ar.jump(n_acc, P.R);
+      apar = (apar + n_acc) & 3;
+    }
+  } else if (warp >= kWorkWarp0) {
+    // ============================================================ A-stage workers
+    const int aw = warp - kWorkWarp0;
+    if (IN == kSPro) {
+      // The raw NHWC bf16 row was delivered by TMA (zero outside the image / beyond Cin).  Apply the dense-block
+      // pre-activation relu(s*x+t) in place in fp32; pixels outside the image stay zero, i.e. the conv padding is applied
+      // AFTER the activation (reference models/cdan.py:41-46).  Thread -> (16-byte channel group u, pixels qb + 32*i).
+      // All four loads are issued before any arithmetic and the four stores follow (the explicit ld/st.shared are
+      // volatile asm and would otherwise serialise load -> math -> store per pixel).
+      const int t = aw * 32 + lane, u = t & 7, qb = t >> 3;
+      const uint32_t sA_u = ptx::smem_u32(sA);
+      uint32_t off[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) off[i] = ptx::sw128_offset(uint32_t(qb + 32 * i), uint32_t(u));
+      float4 s0, s1, t0, t1;
+      int cached_c = -1;
+      Ring st;
+      for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+        const Item it = decode_item(P, item);
+        bool ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int col = SHIFT ? it.w0 - 1 + 30 * i + qb : it.w0 + qb + 32 * i;
+          ok[i] = col >= 0 && col < P.W;
+        }
+        const int j0 = max(it.h0 - PAD, 0), j1 = min(it.h1 + PAD, P.H);
+        for (int j = j0; j < j1; ++j) {
+          for (int c = 0; c < P.nchunks; ++c) {
+            if (c != cached_c) {
+              s0 = *reinterpret_cast<const float4*>(s_pre_s + c * 64 + u * 8);
+              s1 = *reinterpret_cast<const float4*>(s_pre_s + c * 64 + u * 8 + 4);
+              t0 = *reinterpret_cast<const float4*>(s_pre_t + c * 64 + u * 8);
+              t1 = *reinterpret_cast<const float4*>(s_pre_t + c * 64 + u * 8 + 4);
+              cached_c = c;
+            }
+            const bool active = u * 8 < min(64, P.Cin - c * 64);
+            ptx::mbar_wait(&raw_full[st.i], st.w & 1);
+            if (active) {
+              const uint32_t base = sA_u + uint32_t(st.i) * kStage;
+              uint4 r[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) r[i] = ptx::lds128(base + off[i]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                r[i].x = bf2(fmaxf(fmaf(bflo(r[i].x), s0.x, t0.x), 0.f), fmaxf(fmaf(bfhi(r[i].x), s0.y, t0.y), 0.f));
+                r[i].y = bf2(fmaxf(fmaf(bflo(r[i].y), s0.z, t0.z), 0.f), fmaxf(fmaf(bfhi(r[i].y), s0.w, t0.w), 0.f));
+                r[i].z = bf2(fmaxf(fmaf(bflo(r[i].z), s1.x, t1.x), 0.f), fmaxf(fmaf(bfhi(r[i].z), s1.y, t1.y), 0.f));
+                r[i].w = bf2(fmaxf(fmaf(bflo(r[i].w), s1.z, t1.z), 0.f), fmaxf(fmaf(bfhi(r[i].w), s1.w, t1.w), 0.f));
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (ok[i]) ptx::sts128(base + off[i], r[i]);  // out-of-image pixels keep TMA's zero fill
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&a_full[st.i]);
+            st.step(P.SA);
+          }
+        }
+      }
+    } else if (IN == kSNchw) {
+      // encoder.conv1: the planar fp32 row (3 channels x 136 pixels from column w0-4, zero filled outside the image by TMA) waits in the
+      // raw ring; build the K-folded bf16 row A[p][s*3+ci] = x[ci][j][w0+p-1+s], one thread per strip pixel.
+      const int p = aw * 32 + lane;
+      const uint32_t sA_u = ptx::smem_u32(sA);
+      Ring st, rr;
+      for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+        const Item it = decode_item(P, item);
+        const int j0 = max(it.h0 - 1, 0), j1 = min(it.h1 + 1, P.H);
+        for (int j = j0; j < j1; ++j) {
+          ptx::mbar_wait(&raw_full[rr.i], rr.w & 1);
+          const float* raw = s_raw + rr.i * kRawFloats + p + 3;
+          float x[9];
+#pragma unroll
+          for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) x[s * 3 + ci] = raw[ci * kRawW + s];
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&raw_empty[rr.i]);
+          ptx::mbar_wait(&a_empty[st.i], (st.w & 1) ^ 1);
+          const uint32_t base = sA_u + uint32_t(st.i) * kStage;
+          ptx::sts128(base + ptx::sw128_offset(uint32_t(p), 0),
+                      make_uint4(bf2(x[0], x[1]), bf2(x[2], x[3]), bf2(x[4], x[5]), bf2(x[6], x[7])));
+          ptx::sts128(base + ptx::sw128_offset(uint32_t(p), 1), make_uint4(bf2(x[8], 0.f), 0u, 0u, 0u));
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&a_full[st.i]);
+          st.step(P.SA);
+          rr.step(kRawStages);
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled stream_get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    void* p = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+constexpr int kSmemLimit = 232448 - 2048;  // 227 KB opt-in maximum minus static shared (barriers) and alignment slack
+
+void put_bf16(uint8_t* blk, int row, int k, float val) {
+  const bf16 b = __float2bfloat16_rn(val);
+  std::memcpy(blk + ptx::sw128_offset(uint32_t(row), uint32_t(k >> 3)) + (k & 7) * 2, &b, 2);
+}
+
+int stream_nt(int Cout, int ks) {
+  if (Cout <= 16) return 16;
+  if (ks == 3) return 0;  // folded 3x3 only for 16-wide outputs (ring = 32 slots); wider 3x3 use the tile kernel
+  if (Cout <= 64) return 64;
+  return 128;
+}
+
+}  // namespace
+
+int stream_pack_create(const float* w, const float* bias, int Cin, int Cout, int CoutP, int ks, StreamPack** out) {
+  *out = nullptr;
+  if (ks != 1 && ks != 3) return fail("stream_pack: ks must be 1 or 3");
+  StreamPack* p = new StreamPack();
+  p->Cin = Cin; p->Cout = Cout; p->ks = ks;
+  p->nchunks = (Cin + 63) / 64;
+  p->NT = stream_nt(Cout, ks);
+  std::vector<uint8_t> img;
+  std::vector<float> hb;
+  if (p->NT) {
+    // 3x3: one [144 x 64ch] block per K-chunk, rows n = pos*48 + s*16 + co with window position pos <-> kernel row
+    // r = 2 - pos (input row j feeds output rows j-1+pos) and s the horizontal tap; 1x1: rows n = co.
+    const int NT = p->NT, NMMA = ks == 3 ? 9 * NT : NT;
+    p->npass = (Cout + NT - 1) / NT;
+    const size_t block = size_t(NMMA) * 128;
+    p->pass_bytes = size_t(p->nchunks) * block;
+    img.assign(p->pass_bytes * p->npass, 0);
+    hb.assign(size_t(p->npass) * NT, 0.f);
+    for (int pass = 0; pass < p->npass; ++pass)
+      for (int c = 0; c < p->nchunks; ++c) {
+        uint8_t* blk = img.data() + pass * p->pass_bytes + size_t(c) * block;
+        for (int pos = 0; pos < (ks == 3 ? 3 : 1); ++pos)
+          for (int s = 0; s < (ks == 3 ? 3 : 1); ++s)
+            for (int nn = 0; nn < NT; ++nn) {
+              const int co = pass * NT + nn;
+              if (co >= Cout) continue;
+              const int tap = ks == 3 ? (2 - pos) * 3 + s : 0;
+              for (int k = 0; k < 64; ++k) {
+                const int ci = c * 64 + k;
+                if (ci >= Cin) continue;
+                put_bf16(blk, (pos * 3 + s) * NT + nn, k, w[(size_t(tap) * Cin + ci) * CoutP + co]);
+              }
+            }
+      }
+    for (int co = 0; co < Cout; ++co) hb[co] = bias[co];
+    if (cudaMalloc(&p->d_w, img.size()) != cudaSuccess ||
+        cudaMemcpy(p->d_w, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      stream_pack_destroy(p);
+      return fail("stream_pack: weight upload failed");
+    }
+  }
+  if (ks == 3 && Cin == 3 && Cout <= 64) {  // conv1: horizontal taps folded into K, vertical taps into N (NT = 64)
+    std::vector<uint8_t> k(size_t(192) * 128, 0);
+    for (int pos = 0; pos < 3; ++pos)
+      for (int co = 0; co < Cout; ++co)
+        for (int s = 0; s < 3; ++s)
+          for (int ci = 0; ci < 3; ++ci)
+            put_bf16(k.data(), pos * 64 + co, s * 3 + ci, w[(size_t((2 - pos) * 3 + s) * Cin + ci) * CoutP + co]);
+    if (hb.empty()) {
+      hb.assign(64, 0.f);
+      for (int co = 0; co < Cout; ++co) hb[co] = bias[co];
+    }
+    if (cudaMalloc(&p->d_wk, k.size()) != cudaSuccess ||
+        cudaMemcpy(p->d_wk, k.data(), k.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      stream_pack_destroy(p);
+      return fail("stream_pack: weight upload failed");
+    }
+  }
+  if (!hb.empty()) {
+    hb.resize(std::max<size_t>(hb.size(), 64), 0.f);
+    if (cudaMalloc(&p->d_bias, hb.size() * 4) != cudaSuccess ||
+        cudaMemcpy(p->d_bias, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+      stream_pack_destroy(p);
+      return fail("stream_pack: bias upload failed");
+    }
+  }
+  *out = p;
+  return 0;
+}
+
+void stream_pack_destroy(StreamPack* p) {
+  if (!p) return;
+  if (p->d_w) cudaFree(p->d_w);
+  if (p->d_wk) cudaFree(p->d_wk);
+  if (p->d_bias) cudaFree(p->d_bias);
+  delete p;
+}
+
+bool conv_stream_supported(const ConvDesc& d, const StreamPack& pk) {
+  if (d.in_nchw) return pk.d_wk && d.Cin == 3 && d.W % 4 == 0 && !d.pre_scale && !d.out_nchw && d.out_ld % 8 == 0 && (!d.pool || !((d.H | d.W) & 1));
+  if (!pk.d_w || pk.NT == 0) return false;
+  if (d.Cin % 8 != 0 || d.in_ld % 8 != 0 || d.pool) return false;
+  if (d.out_nchw) return d.Cout <= 16;
+  return d.out_ld % 8 == 0;
+}
+
+int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t stream) {
+  if (!conv_stream_supported(d, pk)) return fail("conv_stream: unsupported convolution shape");
+  const bool kfold = d.in_nchw != nullptr;
+  const int in_mode = kfold ? kSNchw : (d.pre_scale ? kSPro : kSTma);
+  const int fold = d.ks == 3 ? 3 : 1;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+  SParams P{};
+  P.N = d.N; P.H = d.H; P.W = d.W; P.Cin = d.Cin;
+  P.pad = fold == 3 ? 1 : 0;
+  P.NT = kfold ? 64 : pk.NT;
+  const bool shift = fold == 3 && !kfold;
+  P.NMMA = shift ? 9 * P.NT : fold * P.NT;
+  P.SW = shift ? 3 * P.NT : P.NT;
+  P.R = fold == 3 ? std::min(30, 512 / P.SW - 2) : std::min(kMaxR, 512 / P.NT);
+  P.nchunks = kfold ? 1 : pk.nchunks;
+  P.nS = 1;
+  const int tw_max = shift ? 120 : 128;
+  P.strips = ceil_div(d.W, tw_max);
+  P.TW = std::min(tw_max, kfold ? (ceil_div(d.W, P.strips) + 3) & ~3 : (ceil_div(d.W, P.strips) + 1) & ~1);
+  const int want_segs = std::max(1, ceil_div(sms * 8, d.N * P.strips));
+  P.SEG = std::max(std::min(32, d.H), (ceil_div(d.H, want_segs) + 1) & ~1);
+  P.segs = ceil_div(d.H, P.SEG);
+  P.nitems = d.N * P.strips * P.segs;
+  P.relu = d.relu; P.sigmoid = d.sigmoid; P.Cout = d.Cout;
+  P.in = reinterpret_cast<const bf16*>(d.in); P.in_ld = d.in_ld;
+  P.in_nchw = d.in_nchw; P.pre_s = d.pre_scale; P.pre_t = d.pre_shift;
+  P.out_ld = d.out_ld; P.out_nchw = d.out_nchw;
+  P.wbytes = uint32_t(kfold ? size_t(192) * 128 : pk.pass_bytes);
+  const int tail = 2 * P.nchunks * 64 * 4 + std::max(P.NT, 64) * 4 + 256 + (kfold ? kRawStages * kRawFloats * 4 + 128 : 0);
+  P.SA = std::min(kMaxSA, (kSmemLimit - 1024 - int(P.wbytes) - tail) / kStage);
+  if (P.SA < 3) return fail("conv_stream: weights leave no room for the activation pipeline");
+  const int smem_bytes = P.SA * kStage + 1024 + int(P.wbytes) + tail + 1024;
+
+  CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof(tmap));
+  if (in_mode != kSNchw) {
+    PFN_encodeTiled enc = stream_get_encode();
+    if (!enc) return fail("conv_stream: cuTensorMapEncodeTiled is not available from the driver");
+    if (reinterpret_cast<uintptr_t>(d.in) % 16 != 0) return fail("conv_stream: input pointer must be 16-byte aligned");
+    cuuint64_t gdim[4] = {cuuint64_t(d.Cin), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.N)};
+    cuuint64_t gstr[3] = {cuuint64_t(d.in_ld) * 2, cuuint64_t(d.W) * d.in_ld * 2, cuuint64_t(d.H) * d.W * d.in_ld * 2};
+    cuuint32_t box[4] = {64, cuuint32_t(shift ? 32 : 128), 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.in), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("conv_stream: cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
+  }
+  if (in_mode == kSNchw) {
+    PFN_encodeTiled enc = stream_get_encode();
+    if (!enc) return fail("conv_stream: cuTensorMapEncodeTiled is not available from the driver");
+    if (reinterpret_cast<uintptr_t>(d.in_nchw) % 16 != 0 || d.W % 4 != 0)
+      return fail("conv_stream: planar fp32 input must be 16-byte aligned with W a multiple of 4");
+    cuuint64_t gdim[4] = {cuuint64_t(d.W), cuuint64_t(d.H), 3, cuuint64_t(d.N)};
+    cuuint64_t gstr[3] = {cuuint64_t(d.W) * 4, cuuint64_t(d.H) * d.W * 4, cuuint64_t(3) * d.H * d.W * 4};
+    cuuint32_t box[4] = {cuuint32_t(kRawW), 1, 3, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d.in_nchw), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("conv_stream: cuTensorMapEncodeTiled (fp32 input) failed with code " + std::to_string(int(r)));
+  }
+  const int grid = std::min(P.nitems, sms);
+  const int threads = 32 * (kEpiWarp0 + epi_warps(in_mode) + work_warps(in_mode));
+  const int npass = kfold ? 1 : pk.npass;
+  for (int pass = 0; pass < npass; ++pass) {
+    P.wpack = kfold ? pk.d_wk : pk.d_w + size_t(pass) * pk.pass_bytes;
+    P.bias = pk.d_bias + size_t(pass) * P.NT;
+    P.Cout = std::min(P.NT, d.Cout - pass * P.NT);
+    P.out = reinterpret_cast<bf16*>(d.out) + size_t(pass) * P.NT;
+    auto launch = [&](auto kern) -> int {
+      CDAN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      kern<<<grid, threads, smem_bytes, stream>>>(tmap, P);
+      CDAN_CUDA_OK(cudaGetLastError());
+      return 0;
+    };
+    int rc;
+    if (kfold) rc = d.pool ? launch(conv_stream_kernel<kSNchw, 3, kSPool>) : launch(conv_stream_kernel<kSNchw, 3, kSStore>);
+    else if (fold == 3) {
+      if (d.out_nchw) rc = in_mode == kSPro ? launch(conv_stream_kernel<kSPro, 3, kSNchwOut>) : launch(conv_stream_kernel<kSTma, 3, kSNchwOut>);
+      else rc = in_mode == kSPro ? launch(conv_stream_kernel<kSPro, 3, kSStore>) : launch(conv_stream_kernel<kSTma, 3, kSStore>);
+    } else {
+      if (d.out_nchw) rc = in_mode == kSPro ? launch(conv_stream_kernel<kSPro, 1, kSNchwOut>) : launch(conv_stream_kernel<kSTma, 1, kSNchwOut>);
+      else rc = in_mode == kSPro ? launch(conv_stream_kernel<kSPro, 1, kSStore>) : launch(conv_stream_kernel<kSTma, 1, kSStore>);
+    }
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace cdan

@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -32,6 +33,7 @@ struct UmmaPack {
   uint8_t* d_w = nullptr;   // [npass][chunk][tap][NT rows][128 B swizzled]
   float* d_bias = nullptr;  // [npass*NT]
   int Cin = 0, Cout = 0, ks = 3, NT = 0, npass = 1, nchunks = 0;
+  StreamPack* stream = nullptr;  // streaming-kernel image of the same weights (narrow-output layers)
 };
 
 namespace {
@@ -522,12 +524,17 @@ int umma_pack_create(const float* w, const float* bias, int Cin, int Cout, int C
     umma_pack_destroy(p);
     return fail("umma_pack: upload failed");
   }
+  if (stream_pack_create(w, bias, Cin, Cout, CoutP, ks, &p->stream) != 0) {
+    umma_pack_destroy(p);
+    return -1;
+  }
   *out = p;
   return 0;
 }
 
 void umma_pack_destroy(UmmaPack* p) {
   if (!p) return;
+  stream_pack_destroy(p->stream);
   if (p->d_w) cudaFree(p->d_w);
   if (p->d_bias) cudaFree(p->d_bias);
   delete p;
@@ -546,6 +553,8 @@ bool conv_umma_supported(const ConvDesc& d) {
 int conv_umma_launch(const ConvDesc& d, const UmmaPack& pk, cudaStream_t stream) {
   if (!conv_umma_supported(d)) return fail("conv_umma: unsupported convolution shape");
   if (pk.Cin != d.Cin || pk.Cout != d.Cout || pk.ks != d.ks) return fail("conv_umma: weight pack does not match");
+  static const bool use_stream = !(getenv("CDAN_CONV_STREAM") && atoi(getenv("CDAN_CONV_STREAM")) == 0);
+  if (use_stream && pk.stream && conv_stream_supported(d, *pk.stream)) return conv_stream_launch(d, *pk.stream, stream);
   const int in_mode = d.in_nchw ? kInNchw3 : (d.pre_scale ? kInPro : kInTma);
   TileCfg tc;
   if (!choose_tiles(d, pk.NT, in_mode, &tc)) return fail("conv_umma: no tile configuration fits shared memory");
@@ -578,7 +587,7 @@ int conv_umma_launch(const ConvDesc& d, const UmmaPack& pk, cudaStream_t stream)
     cuuint32_t box[4] = {64, cuuint32_t(tc.WP), cuuint32_t(tc.TH + 2 * P.halo), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.in), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("conv_umma: cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
   }

@@ -12,6 +12,14 @@ int umma_pack_create(const float* w_taps_cin_coutp, const float* bias_coutp, int
 void umma_pack_destroy(UmmaPack* p);
 
 bool conv_umma_supported(const ConvDesc& d);
+
+// Streaming, tap-folded variant (conv_stream.cu) used for the narrow-output layers; conv_umma_launch dispatches to it.
+struct StreamPack;
+int stream_pack_create(const float* w_taps_cin_coutp, const float* bias_coutp, int Cin, int Cout, int CoutP, int ks,
+                       StreamPack** out);
+void stream_pack_destroy(StreamPack* p);
+bool conv_stream_supported(const ConvDesc& d, const StreamPack& pack);
+int conv_stream_launch(const ConvDesc& d, const StreamPack& pack, cudaStream_t stream);
 int conv_umma_launch(const ConvDesc& d, const UmmaPack& pack, cudaStream_t stream);
 
 }  // namespace cdan

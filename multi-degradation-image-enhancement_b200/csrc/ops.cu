@@ -39,14 +39,17 @@ int cdan_op_conv2d(int dtype, int impl, void* stream, const float* x, int N, int
   cudaStream_t s = (cudaStream_t)stream;
   const DType dt = DType(dtype);
   Scratch sc;
-  const int CinP = int(align_up(size_t(Cin), 16)), CoutP = int(align_up(size_t(Cout), 16));
+  // A 3-channel 3x3 convolution on the tcgen05 path reads the caller's planar fp32 tensor directly, exactly like
+  // encoder.conv1 does inside cdan_forward (no NHWC staging copy).
+  const bool nchw_in = Cin == 3 && ks == 3 && !pre_scale && impl == 0 && dt == kBF16;
+  const int CinP = nchw_in ? Cin : int(align_up(size_t(Cin), 16)), CoutP = int(align_up(size_t(Cout), 16));
   const int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W;
   void *xin, *yout;
   float *dw, *db, *dps = nullptr, *dpt = nullptr;
   CDAN_TRY(sc.alloc(&xin, size_t(N) * H * W * CinP * esize(dtype)));
   CDAN_TRY(sc.alloc(&yout, size_t(N) * OH * OW * CoutP * esize(dtype)));
   CDAN_CUDA_OK(cudaMemsetAsync(xin, 0, size_t(N) * H * W * CinP * esize(dtype), s));
-  CDAN_TRY(nchw_to_nhwc_launch(dt, x, xin, CinP, N, Cin, H, W, s));
+  if (!nchw_in) CDAN_TRY(nchw_to_nhwc_launch(dt, x, xin, CinP, N, Cin, H, W, s));
   // pack weights on the host: [taps][CinP][CoutP]
   const int taps = ks * ks;
   std::vector<float> hw(size_t(Cout) * Cin * taps), hb(CoutP, 0.f), pw(size_t(taps) * CinP * CoutP, 0.f);
@@ -74,6 +77,7 @@ int cdan_op_conv2d(int dtype, int impl, void* stream, const float* x, int N, int
   ConvDesc d;
   d.N = N; d.H = H; d.W = W; d.Cin = CinP; d.Cout = Cout; d.ks = ks;
   d.in = xin; d.in_ld = CinP;
+  if (nchw_in) d.in_nchw = x;
   d.pre_scale = dps; d.pre_shift = dpt;
   d.w = dw; d.CoutP = CoutP; d.bias = db;
   d.relu = relu; d.pool = pool;
@@ -83,7 +87,10 @@ int cdan_op_conv2d(int dtype, int impl, void* stream, const float* x, int N, int
     UmmaPack* pk = nullptr;
     CDAN_TRY(umma_pack_create(pw.data(), hb.data(), CinP, Cout, CoutP, ks, &pk));
     int rc = conv_umma_launch(d, *pk, s);
-    if (rc == 0 && cudaStreamSynchronize(s) != cudaSuccess) rc = fail("cdan_op_conv2d: tcgen05 kernel failed");
+    if (rc == 0) {
+      cudaError_t e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) rc = fail(std::string("cdan_op_conv2d: tcgen05 kernel failed: ") + cudaGetErrorString(e));
+    }
     umma_pack_destroy(pk);
     if (rc) return rc;
   } else {

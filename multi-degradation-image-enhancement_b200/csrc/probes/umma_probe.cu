@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(128) k_probe_rate(int N, int reps, long long* 
           ptx::umma_bf16(d, hi | (a + 4), hi | (b0 + 4), idesc, 1u);
           ptx::umma_bf16(d, hi | (a + 6), hi | (b0 + 6), idesc, 1u);
           a += 1024;
-          d += (N < 128 ? N : 128) * (N <= 128 ? 1 : 0);
+          d += (4 * N <= 512) ? N : 0;
         }
       }
       ptx::umma_commit(&bar);
@@ -201,6 +201,91 @@ __global__ void __launch_bounds__(128) k_probe_rate(int N, int reps, long long* 
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc(tmem, 512);
+}
+
+
+// ------------------------------------------------------------------------------------------------ T4
+// TMEM read / clear throughput: `nwarps` warps (warp w owns lane quarter w%4) stream over `cols` columns `reps` times
+// with tcgen05.ld.32x32b.x16 (mode 0), .x16 followed by a tcgen05.st of zeros to the same columns (mode 1).
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(0u)
+      : "memory");
+}
+__global__ void __launch_bounds__(256) k_probe_tmem(int mode, int cols, int reps, long long* cycles_out, float* sink) {
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid / 32;
+  if (warp == 0) { ptx::tmem_alloc(&tmem_base_s, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s + (uint32_t((warp & 3) * 32) << 16);
+  const int half = (blockDim.x > 128) ? (warp >> 2) : 0, nhalf = blockDim.x > 128 ? 2 : 1;
+  float acc = 0.f;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int r = 0; r < reps; ++r) {
+    for (int c = half * 16; c < cols; c += 16 * nhalf) {
+      uint32_t v[16];
+      ptx::tmem_ld16(tmem + c, v);
+      ptx::tmem_wait_ld();
+      if (mode == 1) {
+        tmem_st16_zero(tmem + c);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc += __uint_as_float(v[j]);
+    }
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  if (tid == 0) cycles_out[blockIdx.x] = t1 - t0;
+  if (acc == 123.456f) sink[tid] = acc;
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base_s, 512);
+}
+// mode 2: two loads in flight before the wait (x16 + x16); mode 3: one x32 load
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__global__ void __launch_bounds__(256) k_probe_tmem32(int cols, int reps, long long* cycles_out, float* sink) {
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid / 32;
+  if (warp == 0) { ptx::tmem_alloc(&tmem_base_s, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s + (uint32_t((warp & 3) * 32) << 16);
+  const int half = (blockDim.x > 128) ? (warp >> 2) : 0, nhalf = blockDim.x > 128 ? 2 : 1;
+  float acc = 0.f;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int r = 0; r < reps; ++r) {
+    for (int c = half * 32; c < cols; c += 32 * nhalf) {
+      uint32_t v[32];
+      tmem_ld32(tmem + c, v);
+      ptx::tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc += __uint_as_float(v[j]);
+    }
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  if (tid == 0) cycles_out[blockIdx.x] = t1 - t0;
+  if (acc == 123.456f) sink[tid] = acc;
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base_s, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -357,7 +442,7 @@ int main() {
     CK(cudaMalloc(&dC, 148 * 8));
     const int smem_bytes = 1024 + 65536 + 32768 + 1024;
     CK(cudaFuncSetAttribute(k_probe_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    for (int N : {16, 32, 64, 128, 256}) {
+    for (int N : {16, 32, 48, 64, 96, 128, 144, 192, 256}) {
       const int reps = 500;  // 500 * 16 = 8000 MMAs
       for (int it = 0; it < 2; ++it) {
         k_probe_rate<<<148, 128, smem_bytes>>>(N, reps, dC);
@@ -371,6 +456,30 @@ int main() {
              N / 2.0, 100.0 * (N / 2.0) / (avg / (reps * 16.0)));
     }
     cudaFree(dC);
+  }
+
+  // ---------------- T4
+  {
+    long long* dC; float* dS;
+    CK(cudaMalloc(&dC, 148 * 8));
+    CK(cudaMalloc(&dS, 1024 * 4));
+    for (int threads : {128, 256})
+      for (int mode : {0, 1, 3}) {
+        const int reps = 200, cols = 512;
+        for (int it = 0; it < 2; ++it) {
+          if (mode == 3) k_probe_tmem32<<<148, threads>>>(cols, reps, dC, dS);
+          else k_probe_tmem<<<148, threads>>>(mode, cols, reps, dC, dS);
+          cudaError_t e = cudaDeviceSynchronize();
+          if (e != cudaSuccess) { printf("T4 CUDA ERROR %s\n", cudaGetErrorString(e)); return 8; }
+        }
+        std::vector<long long> c(148);
+        CK(cudaMemcpy(c.data(), dC, 148 * 8, cudaMemcpyDeviceToHost));
+        double avg = 0; for (auto v : c) avg += v; avg /= 148;
+        const double bytes = double(reps) * 128 * cols * 4;
+        printf("T4 threads=%d mode=%d (%s): %.1f B/cycle/SM TMEM, %.1f cycles per 128x16 block\n", threads, mode,
+               mode == 0 ? "ld.x16" : mode == 1 ? "ld.x16+st.x16 zero" : "ld.x32", bytes / avg, avg / (reps * cols / 16.0));
+      }
+    cudaFree(dC); cudaFree(dS);
   }
   printf("probe done\n");
   return 0;

@@ -68,10 +68,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef CDAN_MBAR_MAX_POLLS
 #define CDAN_MBAR_MAX_POLLS (1u << 26)
 #endif
-__device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
   printf("cdan_b200: mbarrier timeout block=(%d,%d) thread=%d smem=0x%x parity=%u\n", blockIdx.x, blockIdx.y,
          threadIdx.x, smem_u32(bar), parity);
+#ifdef CDAN_MBAR_DEBUG
+  asm volatile("exit;");  // debug builds: let the kernel drain so the printf buffer reaches the host
+#else
   __trap();
+#endif
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t polls = 0;
@@ -175,6 +179,39 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr)
                : "memory");
+}
+
+
+// Zero this warp's 32 lanes x 16 consecutive TMEM columns (used to re-arm ring accumulators after they were read).
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(
+          taddr),
+      "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 16-byte streaming global load: read-only path, no L1 allocation (each activation byte is used once per CTA).
+__device__ __forceinline__ uint4 ldg_stream128(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// Explicit shared-window accesses (32-bit shared address): keeps the compiler from falling back to generic LD/ST.
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // Byte offset of the 16-byte chunk `chunk16` (0..7) of row `row` inside a 128B-swizzled K-major tile whose

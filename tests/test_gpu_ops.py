@@ -42,6 +42,17 @@ CONV_CASES = [
     (1, 256, 512, 8, 8, 3, False, True, False),   # encoder.conv4
     (1, 512, 256, 5, 7, 3, False, True, False),   # odd spatial extent
     (3, 128, 64, 135 // 5, 16, 3, False, True, False),
+    # larger extents: several column strips / row segments of the streaming kernel, ring wrap-around, N passes
+    (1, 16, 16, 70, 300, 3, True, False, False),   # final_dense layer 0 class, 3 strips x 3 segments
+    (2, 48, 16, 45, 130, 3, True, False, False),
+    (1, 304, 16, 40, 24, 3, True, False, False),   # dense3 layer 3 (5 K-chunks)
+    (2, 3, 64, 72, 260, 3, False, True, True),     # encoder.conv1: planar fp32 input, K-folded taps, fused pool
+    (1, 3, 64, 38, 50, 3, False, True, False),
+    (1, 128, 64, 40, 200, 1, True, False, False),  # transition, 2 strips
+    (1, 320, 256, 24, 136, 1, True, False, False), # dense3 transition: two 128-channel passes
+    (1, 64, 3, 40, 140, 3, False, True, False),    # decoder.conv4
+    (1, 64, 128, 36, 250, 3, False, True, True),   # encoder.conv2, several tiles
+    (1, 128, 64, 33, 150, 3, False, True, False),  # decoder.conv3
 ]
 
 
