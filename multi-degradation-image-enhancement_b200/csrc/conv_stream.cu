@@ -55,10 +55,11 @@ constexpr int kMaxSA = 12;
 constexpr int kRawStages = 8, kRawW = 136, kRawFloats = 512;
 constexpr int kMaxR = 32;
 // Warp layout: warps 0-3 control, 4-11 epilogue (two groups of four alternating accumulator rows), then the A-stage
-// workers (8 warps for the dense pre-activation, 4 for conv1's row builder, none for TMA-fed layers).
+// workers (16 warps = two groups alternating stages for the dense pre-activation, 4 for conv1's row builder, none for
+// TMA-fed layers).
 constexpr int kEpiWarp0 = 4;
 __host__ __device__ constexpr int epi_warps(int) { return 8; }
-__host__ __device__ constexpr int work_warps(int in_mode) { return in_mode == 0 ? 0 : (in_mode == 1 ? 8 : 4); }
+__host__ __device__ constexpr int work_warps(int in_mode) { return in_mode == 0 ? 0 : (in_mode == 1 ? 16 : 4); }
 
 struct SParams {
   int N, H, W, Cin;
@@ -114,7 +115,7 @@ struct Ring {
 };
 
 template <int IN, int FOLD, int EPI>
-__global__ void __launch_bounds__(640, 1) conv_stream_kernel(const __grid_constant__ CUtensorMap tmapA, const SParams P) {
+__global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(IN)), 1) conv_stream_kernel(const __grid_constant__ CUtensorMap tmapA, const SParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -134,10 +135,11 @@ __global__ void __launch_bounds__(640, 1) conv_stream_kernel(const __grid_consta
   // SHIFT: all nine taps folded into N (N = 9*NT); lane l of warp-quarter q holds strip pixel 30*q + l - 1, the
   // epilogue adds the three horizontal-tap column groups of lanes l-1, l, l+1 (valid outputs: l = 1..30).
   constexpr bool SHIFT = FOLD == 3 && IN != kSNchw;
+  constexpr bool RELU = IN != kSPro;  // dense-block layers have no output ReLU; ConvBlock / decoder convs always do
 
   if (tid == 0) {
     for (int i = 0; i < kMaxSA; ++i) {
-      ptx::mbar_init(&a_full[i], IN == kSTma ? 1 : kWorkWarps);
+      ptx::mbar_init(&a_full[i], IN == kSTma ? 1 : (IN == kSPro ? 8 : 4));
       ptx::mbar_init(&a_empty[i], 1);
       ptx::mbar_init(&raw_full[i], 1);
       if (i < kRawStages) ptx::mbar_init(&raw_empty[i], 4);
@@ -179,50 +181,55 @@ __global__ void __launch_bounds__(640, 1) conv_stream_kernel(const __grid_consta
   ptx::tc_fence_after_sync();
 
   if (warp == 0) {
-    // ============================================================ producer (one thread): resident weights, A rows via TMA
-    if (lane == 0) {
+    // ============================================================ producer: resident weights, then A rows via TMA.
+    // The whole warp walks the loop (uniform control flow); the copies are issued by the elected lane only.
+    const uint32_t leader = ptx::elect_one() ? 1u : 0u;
+    if (leader) {
       ptx::mbar_arrive_expect_tx(&w_full, P.wbytes);
       for (uint32_t off = 0; off < P.wbytes; off += 32768)
         ptx::bulk_g2s(sW + off, P.wpack + off, min(32768u, P.wbytes - off), &w_full);
-      if (IN == kSNchw) {
-        Ring rr;
-        for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-          const Item it = decode_item(P, item);
-          const int j0 = max(it.h0 - 1, 0), j1 = min(it.h1 + 1, P.H);
-          for (int j = j0; j < j1; ++j) {
-            ptx::mbar_wait(&raw_empty[rr.i], (rr.w & 1) ^ 1);
-            ptx::mbar_arrive_expect_tx(&raw_full[rr.i], kRawW * 3 * 4);
-            ptx::tma_load_4d(s_raw + rr.i * kRawFloats, &tmapA, it.w0 - 4, j, 0, it.n, &raw_full[rr.i]);
-            rr.step(kRawStages);
-          }
+    }
+    __syncwarp();
+    if (IN == kSNchw) {
+      Ring rr;
+      for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+        const Item it = decode_item(P, item);
+        const int j0 = max(it.h0 - 1, 0), j1 = min(it.h1 + 1, P.H);
+        for (int j = j0; j < j1; ++j) {
+          ptx::mbar_wait(&raw_empty[rr.i], (rr.w & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx_if(leader, &raw_full[rr.i], kRawW * 3 * 4);
+          ptx::tma_load_4d_if(leader, s_raw + rr.i * kRawFloats, &tmapA, it.w0 - 4, j, 0, it.n, &raw_full[rr.i]);
+          rr.step(kRawStages);
         }
-      } else {
-        Ring st;
-        for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-          const Item it = decode_item(P, item);
-          const int j0 = max(it.h0 - PAD, 0), j1 = min(it.h1 + PAD, P.H);
-          for (int j = j0; j < j1; ++j) {
-            for (int c = 0; c < P.nchunks; ++c) {
-              // kSTma: the row feeds the MMA directly; kSPro: it lands raw and the workers activate it in place
-              uint64_t* full = IN == kSTma ? &a_full[st.i] : &raw_full[st.i];
-              ptx::mbar_wait(&a_empty[st.i], (st.w & 1) ^ 1);
-              ptx::mbar_arrive_expect_tx(full, kStage);
-              uint8_t* dst = sA + size_t(st.i) * kStage;
-              if (SHIFT) {
+      }
+    } else {
+      Ring st;
+      for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+        const Item it = decode_item(P, item);
+        const int j0 = max(it.h0 - PAD, 0), j1 = min(it.h1 + PAD, P.H);
+        for (int j = j0; j < j1; ++j) {
+          for (int c = 0; c < P.nchunks; ++c) {
+            // kSTma: the row feeds the MMA directly; kSPro: it lands raw and the workers activate it in place
+            uint64_t* full = IN == kSTma ? &a_full[st.i] : &raw_full[st.i];
+            ptx::mbar_wait(&a_empty[st.i], (st.w & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx_if(leader, full, kStage);
+            uint8_t* dst = sA + size_t(st.i) * kStage;
+            if (SHIFT) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) ptx::tma_load_4d(dst + q * 4096, &tmapA, c * 64, it.w0 - 1 + 30 * q, j, it.n, full);
-              } else {
-                ptx::tma_load_4d(dst, &tmapA, c * 64, it.w0, j, it.n, full);
-              }
-              st.step(P.SA);
+              for (int q = 0; q < 4; ++q)
+                ptx::tma_load_4d_if(leader, dst + q * 4096, &tmapA, c * 64, it.w0 - 1 + 30 * q, j, it.n, full);
+            } else {
+              ptx::tma_load_4d_if(leader, dst, &tmapA, c * 64, it.w0, j, it.n, full);
             }
+            st.step(P.SA);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer (one thread)
-    if (lane == 0) {
+    // ============================================================ MMA issuer: uniform loop, elected lane issues
+    {
+      const uint32_t leader = ptx::elect_one() ? 1u : 0u;
       const uint32_t idesc = ptx::umma_idesc_bf16(128, P.NMMA);
       const uint64_t desc_hi = ptx::umma_desc_sw128(0, 1024) & 0xffffffff00000000ull;
       const uint32_t flags = uint32_t(ptx::umma_desc_sw128(0, 1024) & 0xffffffffull);
@@ -254,20 +261,21 @@ __global__ void __launch_bounds__(640, 1) conv_stream_kernel(const __grid_consta
 #pragma unroll
               for (int k = 0; k < (IN == kSNchw ? 1 : 4); ++k)
                 if (k < ksteps)
-                  ptx::umma_bf16(dcol, desc_hi | (a0 + uint32_t(2 * k)), desc_hi | (b0 + uint32_t(2 * k)), idesc, k == 0 ? acc0 : 1u);
-              ptx::umma_commit(&a_empty[st.i]);
+                  ptx::umma_bf16_if(leader, dcol, desc_hi | (a0 + uint32_t(2 * k)), desc_hi | (b0 + uint32_t(2 * k)), idesc,
+                                    k == 0 ? acc0 : 1u);
+              ptx::umma_commit_if(leader, &a_empty[st.i]);
               st.step(P.SA);
               b0 += blk16;
             }
           }
-          ptx::umma_commit(&acc_done[dr.i]);
+          ptx::umma_commit_if(leader, &acc_done[dr.i]);
           dr.step(P.R);
           fr.step(P.R);
         }
         if (PAD) {  // the two trailing accumulator rows of the segment receive no further input
-          ptx::umma_commit(&acc_done[dr.i]);
+          ptx::umma_commit_if(leader, &acc_done[dr.i]);
           dr.step(P.R);
-          ptx::umma_commit(&acc_done[dr.i]);
+          ptx::umma_commit_if(leader, &acc_done[dr.i]);
           dr.step(P.R);
           fr.add(2, P.R);
         }
@@ -363,7 +371,7 @@ __global__ void __launch_bounds__(640, 1) conv_stream_kernel(const __grid_consta
               float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y, __uint_as_float(v[2]) + b0.z,
                             __uint_as_float(v[3]) + b0.w, __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
                             __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
-              if (P.relu) {
+              if (RELU) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
               }
@@ -440,7 +448,7 @@ __global__ void __launch_bounds__(640, 1) conv_stream_kernel(const __grid_consta
                   float x = fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e]));
                   x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
                   x += bb[e];  // max commutes with the per-channel bias and with ReLU
-                  m[e] = P.relu ? fmaxf(x, 0.f) : x;
+                  m[e] = RELU ? fmaxf(x, 0.f) : x;
                 }
                 // even lane keeps channels [c0, c0+8), odd lane [c0+8, c0+16) of the pooled pixel
                 if ((lane & 1) == hh) {
@@ -476,7 +484,8 @@ __global__ void __launch_bounds__(640, 1) conv_stream_kernel(const __grid_consta
       // AFTER the activation (reference models/cdan.py:41-46).  Thread -> (16-byte channel group u, pixels qb + 32*i).
       // All four loads are issued before any arithmetic and the four stores follow (the explicit ld/st.shared are
       // volatile asm and would otherwise serialise load -> math -> store per pixel).
-      const int t = aw * 32 + lane, u = t & 7, qb = t >> 3;
+      // Two groups of eight warps take alternate stages.
+      const int grp = aw >> 3, t = (aw & 7) * 32 + lane, u = t & 7, qb = t >> 3;
       const uint32_t sA_u = ptx::smem_u32(sA);
       uint32_t off[4];
 #pragma unroll
@@ -484,6 +493,7 @@ __global__ void __launch_bounds__(640, 1) conv_stream_kernel(const __grid_consta
       float4 s0, s1, t0, t1;
       int cached_c = -1;
       Ring st;
+      int turn = 0;  // stage parity: this group works when turn == grp
       for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
         const Item it = decode_item(P, item);
         bool ok[4];
@@ -494,7 +504,8 @@ __global__ void __launch_bounds__(640, 1) conv_stream_kernel(const __grid_consta
         }
         const int j0 = max(it.h0 - PAD, 0), j1 = min(it.h1 + PAD, P.H);
         for (int j = j0; j < j1; ++j) {
-          for (int c = 0; c < P.nchunks; ++c) {
+          for (int c = 0; c < P.nchunks; ++c, turn ^= 1, st.step(P.SA)) {
+            if (turn != grp) continue;
             if (c != cached_c) {
               s0 = *reinterpret_cast<const float4*>(s_pre_s + c * 64 + u * 8);
               s1 = *reinterpret_cast<const float4*>(s_pre_s + c * 64 + u * 8 + 4);
@@ -511,10 +522,10 @@ __global__ void __launch_bounds__(640, 1) conv_stream_kernel(const __grid_consta
               for (int i = 0; i < 4; ++i) r[i] = ptx::lds128(base + off[i]);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                r[i].x = bf2(fmaxf(fmaf(bflo(r[i].x), s0.x, t0.x), 0.f), fmaxf(fmaf(bfhi(r[i].x), s0.y, t0.y), 0.f));
-                r[i].y = bf2(fmaxf(fmaf(bflo(r[i].y), s0.z, t0.z), 0.f), fmaxf(fmaf(bfhi(r[i].y), s0.w, t0.w), 0.f));
-                r[i].z = bf2(fmaxf(fmaf(bflo(r[i].z), s1.x, t1.x), 0.f), fmaxf(fmaf(bfhi(r[i].z), s1.y, t1.y), 0.f));
-                r[i].w = bf2(fmaxf(fmaf(bflo(r[i].w), s1.z, t1.z), 0.f), fmaxf(fmaf(bfhi(r[i].w), s1.w, t1.w), 0.f));
+                r[i].x = ptx::cvt_relu_bf16x2(fmaf(bflo(r[i].x), s0.x, t0.x), fmaf(bfhi(r[i].x), s0.y, t0.y));
+                r[i].y = ptx::cvt_relu_bf16x2(fmaf(bflo(r[i].y), s0.z, t0.z), fmaf(bfhi(r[i].y), s0.w, t0.w));
+                r[i].z = ptx::cvt_relu_bf16x2(fmaf(bflo(r[i].z), s1.x, t1.x), fmaf(bfhi(r[i].z), s1.y, t1.y));
+                r[i].w = ptx::cvt_relu_bf16x2(fmaf(bflo(r[i].w), s1.z, t1.z), fmaf(bfhi(r[i].w), s1.w, t1.w));
               }
 #pragma unroll
               for (int i = 0; i < 4; ++i)
@@ -523,7 +534,6 @@ __global__ void __launch_bounds__(640, 1) conv_stream_kernel(const __grid_consta
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&a_full[st.i]);
-            st.step(P.SA);
           }
         }
       }
@@ -680,8 +690,9 @@ void stream_pack_destroy(StreamPack* p) {
 }
 
 bool conv_stream_supported(const ConvDesc& d, const StreamPack& pk) {
-  if (d.in_nchw) return pk.d_wk && d.Cin == 3 && d.W % 4 == 0 && !d.pre_scale && !d.out_nchw && d.out_ld % 8 == 0 && (!d.pool || !((d.H | d.W) & 1));
+  if (d.in_nchw) return pk.d_wk && d.Cin == 3 && d.W % 4 == 0 && d.relu && !d.pre_scale && !d.out_nchw && d.out_ld % 8 == 0 && (!d.pool || !((d.H | d.W) & 1));
   if (!pk.d_w || pk.NT == 0) return false;
+  if ((d.relu != 0) != (d.pre_scale == nullptr)) return false;  // ReLU is compiled in per input mode
   if (d.Cin % 8 != 0 || d.in_ld % 8 != 0 || d.pool) return false;
   if (d.out_nchw) return d.Cout <= 16;
   return d.out_ld % 8 == 0;
@@ -734,7 +745,8 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
     cuuint32_t box[4] = {64, cuuint32_t(shift ? 32 : 128), 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.in), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     d.Cin >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : (d.Cin >= 32 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE),
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("conv_stream: cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
   }

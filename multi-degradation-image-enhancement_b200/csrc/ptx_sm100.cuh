@@ -50,14 +50,19 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Suspend-time hint (ns): the hardware parks the waiting thread until the phase completes or the hint expires, so
+// waiting warps do not burn issue slots in a poll loop.
+#ifndef CDAN_MBAR_SUSPEND_NS
+#define CDAN_MBAR_SUSPEND_NS 20000u
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(CDAN_MBAR_SUSPEND_NS)
       : "memory");
   return ok != 0;
 }
@@ -66,7 +71,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // mbar_wait_relaxed: poll with nanosleep back-off — for producer / epilogue warps, so that their polling does not
 //                    steal issue slots from the warps doing real work on the same SM sub-partition.
 #ifndef CDAN_MBAR_MAX_POLLS
-#define CDAN_MBAR_MAX_POLLS (1u << 26)
+#define CDAN_MBAR_MAX_POLLS (1u << 22)
 #endif
 static __device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
   printf("cdan_b200: mbarrier timeout block=(%d,%d) thread=%d smem=0x%x parity=%u\n", blockIdx.x, blockIdx.y,
@@ -212,6 +217,51 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+
+// ---------------------------------------------------------------- predicated single-thread instructions
+// Executed by every lane of a converged warp with warp-uniform operands; only the lane whose `leader` flag is set
+// performs the operation.  Keeping the control flow uniform lets ptxas hold descriptors / barrier addresses in uniform
+// registers instead of wrapping each UTCHMMA / UTCBAR / UTMALDG in a vote + R2UR.BROADCAST loop.
+__device__ __forceinline__ void umma_bf16_if(uint32_t leader, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(uint32_t leader, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_if(uint32_t leader, uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t.reg .b64 st;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(bytes), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_if(uint32_t leader, void* dst_smem, const void* tmap, int c0, int c1, int c2,
+                                               int c3, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n\t}" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "r"(leader)
+      : "memory");
+}
+// two fp32 -> packed bf16x2 (lo in bits 0-15) with ReLU folded into the conversion
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
 // Byte offset of the 16-byte chunk `chunk16` (0..7) of row `row` inside a 128B-swizzled K-major tile whose
