@@ -1,26 +1,30 @@
 // CBAM attention (models/cbam.py:26-95) as HBM-bound kernels over NHWC activations.
-//   pass 1  pool_partial : per-(n,c) sum and max over a slab of pixels  (deterministic 2-stage reduction,
-//                          no float atomics -> bitwise repeatable like the reference under cudnn.deterministic)
+//   pass 1  pool_partial : per-(n,c) sum and max over one pair of image rows (deterministic 2-stage reduction, no float
+//                          atomics -> bitwise repeatable like the reference under cudnn.deterministic).  In the decoder
+//                          this pass is fused into the producer (glue.cu up_add writes the same partials).
 //   pass 2  gate_mlp     : finish the reduction, shared MLP on avg and max, sigmoid  -> gate[n][c]
 //   pass 3  compress     : per-pixel channel max / mean of x*gate (warp-shuffle reduction) -> comp[n,h,w,2]
 //   pass 4  spatial_gate : sigmoid(bn(conv7x7(comp)))                                  -> sgate[n,h,w]
 //   pass 5  apply        : out = ((x*gate)*sgate) [* dense]
+// (Fusing passes 3-5 into one tiled or streaming kernel was measured and is slower on B200: the tiles resident at once
+// exceed the L2, and a per-strip streaming version is latency-bound between its block barriers.)
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace cdan {
 namespace {
 
-constexpr int kPoolPixelsPerBlock = 2048;
 
 template <typename T>
-__global__ void __launch_bounds__(256) pool_partial_kernel(const T* __restrict__ x, int ld, int C, int HW, int nblk,
+__global__ void __launch_bounds__(256) pool_partial_kernel(const T* __restrict__ x, int ld, int C, int HW, int W, int nblk,
                                                             float* __restrict__ psum, float* __restrict__ pmax) {
   extern __shared__ float red[];  // [npl][C] sums then [npl][C] maxes
   const int vecs = C >> 3;
   const int npl = 256 / vecs;  // pixel lanes
   const int vc = threadIdx.x % vecs, pl = threadIdx.x / vecs;
   const int blk = blockIdx.x, n = blockIdx.y;
-  const int chunk = (HW + nblk - 1) / nblk;
+  const int chunk = 2 * W;  // one block per pair of image rows (same partition as the fused producer in glue.cu)
   const int p0 = blk * chunk, p1 = min(HW, p0 + chunk);
   float s[8], m[8];
 #pragma unroll
@@ -210,17 +214,19 @@ inline int grid_for(size_t total, int block = 256, int cap = 148 * 16) {
 
 template <typename T>
 int cbam_typed(const void* x, int x_ld, const void* mul, int mul_ld, void* out, int out_ld, int N, int H, int W, int C,
-               const CbamWeights& wt, const CbamScratch& sc, cudaStream_t s) {
+               const CbamWeights& wt, const CbamScratch& sc, bool pooled, cudaStream_t s) {
   const int HW = H * W;
-  const size_t npix = size_t(N) * HW;
   const int vecs = C / 8;
   const int npl = 256 / vecs;
-  pool_partial_kernel<T><<<dim3(sc.nblk, N), 256, 2 * npl * C * sizeof(float), s>>>((const T*)x, x_ld, C, HW, sc.nblk,
-                                                                                  sc.psum, sc.pmax);
-  CDAN_CUDA_OK(cudaGetLastError());
+  if (!pooled) {
+    pool_partial_kernel<T><<<dim3(sc.nblk, N), 256, 2 * npl * C * sizeof(float), s>>>((const T*)x, x_ld, C, HW, W, sc.nblk,
+                                                                                    sc.psum, sc.pmax);
+    CDAN_CUDA_OK(cudaGetLastError());
+  }
   gate_mlp_kernel<<<N, 256, (2 * C + 2 * (C / 16)) * sizeof(float), s>>>(sc.psum, sc.pmax, sc.nblk, C, HW, wt.w1, wt.b1,
                                                                          wt.w2, wt.b2, sc.gate);
   CDAN_CUDA_OK(cudaGetLastError());
+  const size_t npix = size_t(N) * HW;
   const int lpp = vecs < 32 ? vecs : 32;
   compress_kernel<T><<<grid_for(npix * lpp), 256, 0, s>>>((const T*)x, x_ld, C, HW, npix, sc.gate, sc.comp);
   CDAN_CUDA_OK(cudaGetLastError());
@@ -234,18 +240,14 @@ int cbam_typed(const void* x, int x_ld, const void* mul, int mul_ld, void* out, 
 
 }  // namespace
 
-int cbam_pool_blocks(int HW) {
-  int b = (HW + kPoolPixelsPerBlock - 1) / kPoolPixelsPerBlock;
-  return b < 1 ? 1 : b;
-}
+int cbam_pool_blocks(int H) { return (H + 1) / 2; }  // one partial per pair of image rows
 
 size_t cbam_scratch_floats(int N, int C, int H, int W) {
-  const size_t nblk = cbam_pool_blocks(H * W);
-  return 2 * size_t(N) * nblk * C + size_t(N) * C + 3 * size_t(N) * H * W + 64;
+  return 2 * size_t(N) * cbam_pool_blocks(H) * C + size_t(N) * C + 3 * size_t(N) * H * W + 64;
 }
 
 void cbam_scratch_carve(float* base, int N, int C, int H, int W, CbamScratch* sc) {
-  sc->nblk = cbam_pool_blocks(H * W);
+  sc->nblk = cbam_pool_blocks(H);
   const size_t part = size_t(N) * sc->nblk * C;
   sc->psum = base;
   sc->pmax = base + part;
@@ -257,12 +259,12 @@ void cbam_scratch_carve(float* base, int N, int C, int H, int W, CbamScratch* sc
 }
 
 int cbam_launch(DType dt, const void* x, int x_ld, const void* mul, int mul_ld, void* out, int out_ld, int N, int H,
-                int W, int C, const CbamWeights& wt, const CbamScratch& sc, cudaStream_t s) {
+                int W, int C, const CbamWeights& wt, const CbamScratch& sc, bool pooled, cudaStream_t s) {
   if (C % 64 != 0 || C > 2048) return fail("cbam: gate_channels must be a multiple of 64 (<= 2048) for the CUDA path");
   if ((C & (C - 1)) != 0) return fail("cbam: gate_channels must be a power of two for the CUDA path");
-  if (N > 65535) return fail("cbam: batch too large for one launch");
-  return dt == kF32 ? cbam_typed<float>(x, x_ld, mul, mul_ld, out, out_ld, N, H, W, C, wt, sc, s)
-                    : cbam_typed<bf16>(x, x_ld, mul, mul_ld, out, out_ld, N, H, W, C, wt, sc, s);
+  if (N > 65535) return fail("cbam: batch or image too large for one launch");
+  return dt == kF32 ? cbam_typed<float>(x, x_ld, mul, mul_ld, out, out_ld, N, H, W, C, wt, sc, pooled, s)
+                    : cbam_typed<bf16>(x, x_ld, mul, mul_ld, out, out_ld, N, H, W, C, wt, sc, pooled, s);
 }
 
 }  // namespace cdan

@@ -16,77 +16,147 @@ __device__ __forceinline__ void up_taps(int o, int n_in, int& i0, int& i1, float
   }
 }
 
+// out = (UP ? bilinear_x2(a) : a) + skip.  One block per (image, pair of output rows); a thread owns 8 channels of a
+// 2x2 output quad: the quad's 3x3 input neighbourhood is loaded once (6 loads per output row pair instead of 8 per
+// pixel) and no per-element 64-bit index arithmetic is needed.  Optionally the block also reduces the per-channel sum and
+// max of what it wrote (ChannelGate pooling partials, models/cbam.py:41-45) — deterministic, no float atomics.
 template <typename T, bool UP>
 __global__ void __launch_bounds__(256) up_add_kernel(const T* __restrict__ a, int a_ld, const T* __restrict__ skip,
-                                                      int skip_ld, T* __restrict__ out, int out_ld, int N, int OH,
-                                                      int OW, int C) {
+                                                      int skip_ld, T* __restrict__ out, int out_ld, int OH, int OW,
+                                                      int C, float* __restrict__ psum, float* __restrict__ pmax) {
+  extern __shared__ float red[];  // [npl][C] sums then [npl][C] maxes (only when pooling)
   const int vecs = C >> 3;
-  const size_t total = size_t(N) * OH * OW * vecs;
-  for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total; idx += size_t(gridDim.x) * blockDim.x) {
-    const int v = int(idx % vecs);
-    const size_t pix = idx / vecs;
-    const int ox = int(pix % OW);
-    const int oy = int((pix / OW) % OH);
-    const int n = int(pix / (size_t(OW) * OH));
-    F8 r;
-    if (UP) {
-      const int IH = OH >> 1, IW = OW >> 1;
-      int y0, y1, x0, x1;
-      float wy0, wy1, wx0, wx1;
-      up_taps(oy, IH, y0, y1, wy0, wy1);
-      up_taps(ox, IW, x0, x1, wx0, wx1);
-      const T* base = a + size_t(n) * IH * IW * a_ld + v * 8;
-      const F8 a00 = load8<T>(base + (size_t(y0) * IW + x0) * a_ld);
-      const F8 a01 = load8<T>(base + (size_t(y0) * IW + x1) * a_ld);
-      const F8 a10 = load8<T>(base + (size_t(y1) * IW + x0) * a_ld);
-      const F8 a11 = load8<T>(base + (size_t(y1) * IW + x1) * a_ld);
+  const int npl = 256 / vecs;
+  const int v = threadIdx.x % vecs, pl = threadIdx.x / vecs;
+  const int j = blockIdx.x, n = blockIdx.y;
+  const int IH = UP ? OH >> 1 : OH, IW = UP ? OW >> 1 : OW;
+  const int QW = (OW + 1) >> 1;
+  float s[8], m[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        r.v[j] = wy0 * (wx0 * a00.v[j] + wx1 * a01.v[j]) + wy1 * (wx0 * a10.v[j] + wx1 * a11.v[j]);
-    } else {
-      r = load8<T>(a + pix * a_ld + v * 8);
-    }
+  for (int e = 0; e < 8; ++e) { s[e] = 0.f; m[e] = -INFINITY; }
+  auto emit = [&](int oy, int ox, F8 r) {
+    const size_t pix = (size_t(n) * OH + oy) * OW + ox;
     const F8 sk = load8<T>(skip + pix * skip_ld + v * 8);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r.v[j] += sk.v[j];
+    for (int e = 0; e < 8; ++e) r.v[e] += sk.v[e];
     store8<T>(out + pix * out_ld + v * 8, r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float q = to_f32<T>(from_f32<T>(r.v[e]));  // pool what was stored
+      s[e] += q;
+      m[e] = fmaxf(m[e], q);
+    }
+  };
+  if (pl < npl) {
+    const T* an = a + size_t(n) * IH * IW * a_ld + v * 8;
+    for (int i = pl; i < QW; i += npl) {
+      if (UP) {
+        const int jm = max(j - 1, 0), jp = min(j + 1, IH - 1), im = max(i - 1, 0), ip = min(i + 1, IW - 1);
+        const F8 m0 = load8<T>(an + (size_t(j) * IW + im) * a_ld), m1 = load8<T>(an + (size_t(j) * IW + i) * a_ld),
+                 m2 = load8<T>(an + (size_t(j) * IW + ip) * a_ld);
+        {
+          const F8 t0 = load8<T>(an + (size_t(jm) * IW + im) * a_ld), t1 = load8<T>(an + (size_t(jm) * IW + i) * a_ld),
+                   t2 = load8<T>(an + (size_t(jm) * IW + ip) * a_ld);
+          F8 r0, r1;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {  // row 2j: rows (j-1: .25, j: .75); cols even (i-1: .25, i: .75), odd (i: .75, i+1: .25)
+            r0.v[e] = 0.25f * (0.25f * t0.v[e] + 0.75f * t1.v[e]) + 0.75f * (0.25f * m0.v[e] + 0.75f * m1.v[e]);
+            r1.v[e] = 0.25f * (0.75f * t1.v[e] + 0.25f * t2.v[e]) + 0.75f * (0.75f * m1.v[e] + 0.25f * m2.v[e]);
+          }
+          emit(2 * j, 2 * i, r0);
+          emit(2 * j, 2 * i + 1, r1);
+        }
+        {
+          const F8 b0 = load8<T>(an + (size_t(jp) * IW + im) * a_ld), b1 = load8<T>(an + (size_t(jp) * IW + i) * a_ld),
+                   b2 = load8<T>(an + (size_t(jp) * IW + ip) * a_ld);
+          F8 r0, r1;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {  // row 2j+1: rows (j: .75, j+1: .25)
+            r0.v[e] = 0.75f * (0.25f * m0.v[e] + 0.75f * m1.v[e]) + 0.25f * (0.25f * b0.v[e] + 0.75f * b1.v[e]);
+            r1.v[e] = 0.75f * (0.75f * m1.v[e] + 0.25f * m2.v[e]) + 0.25f * (0.75f * b1.v[e] + 0.25f * b2.v[e]);
+          }
+          emit(2 * j + 1, 2 * i, r0);
+          emit(2 * j + 1, 2 * i + 1, r1);
+        }
+      } else {
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int oy = 2 * j + dy, ox = 2 * i + dx;
+            if (oy < OH && ox < OW) emit(oy, ox, load8<T>(an + (size_t(oy) * IW + ox) * a_ld));
+          }
+      }
+    }
+  }
+  if (psum == nullptr) return;
+  if (pl < npl) {
+    float* rs = red + (pl * C + v * 8);
+    float* rm = red + (npl * C) + (pl * C + v * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { rs[e] = s[e]; rm[e] = m[e]; }
+  }
+  __syncthreads();
+  const int nblk = gridDim.x;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float ss = 0.f, mm = -INFINITY;
+    for (int q = 0; q < npl; ++q) {  // fixed order
+      ss += red[q * C + c];
+      mm = fmaxf(mm, red[npl * C + q * C + c]);
+    }
+    psum[(size_t(n) * nblk + j) * C + c] = ss;
+    pmax[(size_t(n) * nblk + j) * C + c] = mm;
   }
 }
 
-// Final decoder stage: 3 real channels; writes a zero-padded 16-channel pixel (head of the final dense buffer).
+// Final decoder stage (models/cdan.py:153-154): out[n,h,w,0:3] = bilinear_x2(a)[.,0:3] + x_nchw, channels 3..pad_to
+// zero (head of the final dense block's concat buffer).  One block per (image, pair of output rows), one thread per
+// 2x2 output quad: the quad's 3x3 neighbourhood of `a` is read once, x is read and out written row-contiguously.
 template <typename T>
 __global__ void __launch_bounds__(256) up_add_input_kernel(const T* __restrict__ a, int a_ld,
                                                             const float* __restrict__ x, T* __restrict__ out,
-                                                            int out_ld, int pad_to, int N, int OH, int OW) {
-  const size_t total = size_t(N) * OH * OW;
+                                                            int out_ld, int pad_to, int OH, int OW) {
+  const int j = blockIdx.x, n = blockIdx.y;
   const int IH = OH >> 1, IW = OW >> 1;
-  for (size_t pix = blockIdx.x * size_t(blockDim.x) + threadIdx.x; pix < total; pix += size_t(gridDim.x) * blockDim.x) {
-    const int ox = int(pix % OW);
-    const int oy = int((pix / OW) % OH);
-    const int n = int(pix / (size_t(OW) * OH));
-    int y0, y1, x0, x1;
-    float wy0, wy1, wx0, wx1;
-    up_taps(oy, IH, y0, y1, wy0, wy1);
-    up_taps(ox, IW, x0, x1, wx0, wx1);
-    const T* base = a + size_t(n) * IH * IW * a_ld;
-    F8 r;
+  const int jm = max(j - 1, 0), jp = min(j + 1, IH - 1);
+  const T* an = a + size_t(n) * IH * IW * a_ld;
+  const size_t plane = size_t(OH) * OW;
+  const float* xn = x + size_t(n) * 3 * plane;
+  for (int i = threadIdx.x; i < IW; i += 256) {
+    const int im = max(i - 1, 0), ip = min(i + 1, IW - 1);
+    float t[3][3][3];  // [row jm/j/jp][col im/i/ip][channel]
+    const int rows[3] = {jm, j, jp}, cols[3] = {im, i, ip};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r.v[j] = 0.f;
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float a00 = to_f32<T>(base[(size_t(y0) * IW + x0) * a_ld + c]);
-      const float a01 = to_f32<T>(base[(size_t(y0) * IW + x1) * a_ld + c]);
-      const float a10 = to_f32<T>(base[(size_t(y1) * IW + x0) * a_ld + c]);
-      const float a11 = to_f32<T>(base[(size_t(y1) * IW + x1) * a_ld + c]);
-      const float up = wy0 * (wx0 * a00 + wx1 * a01) + wy1 * (wx0 * a10 + wx1 * a11);
-      r.v[c] = up + x[((size_t(n) * 3 + c) * OH + oy) * OW + ox];
-    }
-    T* o = out + pix * out_ld;
-    store8<T>(o, r);
-    F8 z;
+      for (int c = 0; c < 3; ++c) {
+        const T* p = an + (size_t(rows[r]) * IW + cols[c]) * a_ld;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) z.v[j] = 0.f;
-    for (int c = 8; c < pad_to; c += 8) store8<T>(o + c, z);
+        for (int ch = 0; ch < 3; ++ch) t[r][c][ch] = to_f32<T>(p[ch]);
+      }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        // same tap order and weights as the general kernel: even index -> (i-1: .25, i: .75), odd -> (i: .75, i+1: .25)
+        const int r0 = dy ? 1 : 0, r1 = dy ? 2 : 1, c0 = dx ? 1 : 0, c1 = dx ? 2 : 1;
+        const float wy0 = dy ? 0.75f : 0.25f, wy1 = dy ? 0.25f : 0.75f, wx0 = dx ? 0.75f : 0.25f, wx1 = dx ? 0.25f : 0.75f;
+        const int oy = 2 * j + dy, ox = 2 * i + dx;
+        F8 r;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r.v[e] = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float up = wy0 * (wx0 * t[r0][c0][ch] + wx1 * t[r0][c1][ch]) + wy1 * (wx0 * t[r1][c0][ch] + wx1 * t[r1][c1][ch]);
+          r.v[ch] = up + xn[ch * plane + size_t(oy) * OW + ox];
+        }
+        T* o = out + ((size_t(n) * OH + oy) * OW + ox) * out_ld;
+        store8<T>(o, r);
+        F8 z;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) z.v[e] = 0.f;
+        for (int c = 8; c < pad_to; c += 8) store8<T>(o + c, z);
+      }
   }
 }
 
@@ -122,17 +192,19 @@ inline int grid_for(size_t total, int block = 256, int cap = 148 * 16) {
 }  // namespace
 
 int up_add_launch(DType dt, const void* a, int a_ld, const void* skip, int skip_ld, void* out, int out_ld, int N,
-                  int OH, int OW, int C, int up, cudaStream_t s) {
-  if (C % 8) return fail("up_add: C must be a multiple of 8");
+                  int OH, int OW, int C, int up, cudaStream_t s, float* psum, float* pmax) {
+  if (C % 8 || C > 2048) return fail("up_add: C must be a multiple of 8 (<= 2048)");
   if (up && ((OH | OW) & 1)) return fail("up_add: upsampled extent must be even");
-  const size_t total = size_t(N) * OH * OW * (C / 8);
-  const int g = grid_for(total);
+  if (N > 65535) return fail("up_add: batch too large for one launch");
+  const dim3 grid((OH + 1) / 2, N);
+  const int npl = 256 / (C / 8);
+  const size_t smem = psum ? 2 * size_t(npl) * C * sizeof(float) : 0;
   if (dt == kF32) {
-    if (up) up_add_kernel<float, true><<<g, 256, 0, s>>>((const float*)a, a_ld, (const float*)skip, skip_ld, (float*)out, out_ld, N, OH, OW, C);
-    else up_add_kernel<float, false><<<g, 256, 0, s>>>((const float*)a, a_ld, (const float*)skip, skip_ld, (float*)out, out_ld, N, OH, OW, C);
+    if (up) up_add_kernel<float, true><<<grid, 256, smem, s>>>((const float*)a, a_ld, (const float*)skip, skip_ld, (float*)out, out_ld, OH, OW, C, psum, pmax);
+    else up_add_kernel<float, false><<<grid, 256, smem, s>>>((const float*)a, a_ld, (const float*)skip, skip_ld, (float*)out, out_ld, OH, OW, C, psum, pmax);
   } else {
-    if (up) up_add_kernel<bf16, true><<<g, 256, 0, s>>>((const bf16*)a, a_ld, (const bf16*)skip, skip_ld, (bf16*)out, out_ld, N, OH, OW, C);
-    else up_add_kernel<bf16, false><<<g, 256, 0, s>>>((const bf16*)a, a_ld, (const bf16*)skip, skip_ld, (bf16*)out, out_ld, N, OH, OW, C);
+    if (up) up_add_kernel<bf16, true><<<grid, 256, smem, s>>>((const bf16*)a, a_ld, (const bf16*)skip, skip_ld, (bf16*)out, out_ld, OH, OW, C, psum, pmax);
+    else up_add_kernel<bf16, false><<<grid, 256, smem, s>>>((const bf16*)a, a_ld, (const bf16*)skip, skip_ld, (bf16*)out, out_ld, OH, OW, C, psum, pmax);
   }
   CDAN_CUDA_OK(cudaGetLastError());
   return 0;
@@ -141,9 +213,12 @@ int up_add_launch(DType dt, const void* a, int a_ld, const void* skip, int skip_
 int up_add_input_launch(DType dt, const void* a, int a_ld, const float* x_nchw, void* out, int out_ld, int pad_to,
                         int N, int OH, int OW, cudaStream_t s) {
   if (pad_to % 8 || pad_to < 8) return fail("up_add_input: pad_to must be a positive multiple of 8");
-  const int g = grid_for(size_t(N) * OH * OW);
-  if (dt == kF32) up_add_input_kernel<float><<<g, 256, 0, s>>>((const float*)a, a_ld, x_nchw, (float*)out, out_ld, pad_to, N, OH, OW);
-  else up_add_input_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)a, a_ld, x_nchw, (bf16*)out, out_ld, pad_to, N, OH, OW);
+  if (a_ld < 8 || a_ld % 8) return fail("up_add_input: the upsampled tensor must carry a multiple of 8 (>= 8) channels per pixel");
+  if ((OH | OW) & 1) return fail("up_add_input: output extent must be even");
+  if (N > 65535) return fail("up_add_input: batch too large for one launch");
+  const dim3 g(OH / 2, N);
+  if (dt == kF32) up_add_input_kernel<float><<<g, 256, 0, s>>>((const float*)a, a_ld, x_nchw, (float*)out, out_ld, pad_to, OH, OW);
+  else up_add_input_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)a, a_ld, x_nchw, (bf16*)out, out_ld, pad_to, OH, OW);
   CDAN_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -6,8 +6,10 @@ namespace cdan {
 
 // ---- decoder glue (models/cdan.py:130,137-138,145-146,153-154)
 // out = (up ? bilinear_x2(a) : a) + skip ; a is [N,OH/2,OW/2,C] when up else [N,OH,OW,C]; all NHWC.
+// If psum/pmax are given the kernel also writes the ChannelGate pooling partials of `out` (per image, per pair of
+// output rows: [N][cbam_pool_blocks(OH)][C]), saving CBAM's first pass over the tensor.
 int up_add_launch(DType dt, const void* a, int a_ld, const void* skip, int skip_ld, void* out, int out_ld, int N,
-                  int OH, int OW, int C, int up, cudaStream_t s);
+                  int OH, int OW, int C, int up, cudaStream_t s, float* psum = nullptr, float* pmax = nullptr);
 // Final stage: out[n,h,w,0:3] = bilinear_x2(a)[.,0:3] + x_nchw ; out[n,h,w,3:pad_to] = 0.
 int up_add_input_launch(DType dt, const void* a, int a_ld, const float* x_nchw, void* out, int out_ld, int pad_to,
                         int N, int OH, int OW, cudaStream_t s);
@@ -26,19 +28,20 @@ struct CbamWeights {
   float bn_a = 1.f, bn_b = 0.f;  // folded eval BatchNorm2d(1): s = a*conv + b
 };
 struct CbamScratch {
-  float* psum = nullptr;   // [N][nblk][C]
-  float* pmax = nullptr;   // [N][nblk][C]
+  float* psum = nullptr;   // [N][nblk][C]  per-(image, row pair) channel sums
+  float* pmax = nullptr;   // [N][nblk][C]  ... and maxima
   float* gate = nullptr;   // [N][C]
   float* comp = nullptr;   // [N][H][W][2]
   float* sgate = nullptr;  // [N][H][W]
   int nblk = 0;
 };
-int cbam_pool_blocks(int HW);  // partial-reduction blocks per image
+int cbam_pool_blocks(int H);  // partial-reduction blocks per image: one per pair of image rows
 size_t cbam_scratch_floats(int N, int C, int H, int W);
 void cbam_scratch_carve(float* base, int N, int C, int H, int W, CbamScratch* sc);
-// out = SpatialGate(ChannelGate(x)) [* mul]  (mul = dense-block output of the decoder, models/cdan.py:133,141,149)
+// out = SpatialGate(ChannelGate(x)) [* mul]  (mul = dense-block output of the decoder, models/cdan.py:133,141,149).
+// pooled = true: sc.psum / sc.pmax were already written by the kernel that produced x (up_add_launch with pool outputs).
 int cbam_launch(DType dt, const void* x, int x_ld, const void* mul, int mul_ld, void* out, int out_ld, int N, int H,
-                int W, int C, const CbamWeights& wt, const CbamScratch& sc, cudaStream_t s);
+                int W, int C, const CbamWeights& wt, const CbamScratch& sc, bool pooled, cudaStream_t s);
 
 // ---- post-processing on planar fp32 NCHW images (utils/post_processing.py)
 enum PostOp : int { kContrast = 0, kColor = 1, kSharpen = 2, kDenoise = 3 };

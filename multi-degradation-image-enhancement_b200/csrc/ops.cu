@@ -125,7 +125,7 @@ int cdan_op_cbam(int dtype, void* stream, const float* x, int N, int C, int H, i
   const double a = double(bn_host4[0]) / std::sqrt(double(bn_host4[3]) + 1e-5);
   wt.bn_a = float(a);
   wt.bn_b = float(double(bn_host4[1]) - double(bn_host4[2]) * a);
-  CDAN_TRY(cbam_launch(dt, xin, C, min, C, yout, C, N, H, W, C, wt, cs, s));
+  CDAN_TRY(cbam_launch(dt, xin, C, min, C, yout, C, N, H, W, C, wt, cs, false, s));
   CDAN_TRY(nhwc_to_nchw_launch(dt, yout, C, y, N, C, H, W, s));
   CDAN_CUDA_OK(cudaStreamSynchronize(s));
   return 0;

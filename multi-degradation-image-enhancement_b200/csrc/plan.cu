@@ -235,7 +235,7 @@ size_t carve(Buffers& b, char* base, DType dt, int N, int H, int W) {
   b.U3 = take(p2 * 64 * es);
   b.C3 = take(p2 * 64 * es);
   b.T4 = take(p2 * 8 * es);
-  b.FD = take(p1 * 80 * es);
+  b.FD = take(p1 * 80 * es);  // final dense block concat: 3 input channels padded to 16 (32-byte sectors), then 4 x 16
   size_t sc = 0;
   sc = std::max(sc, cbam_scratch_floats(N, 512, H / 8, W / 8));
   sc = std::max(sc, cbam_scratch_floats(N, 256, H / 8, W / 8));
@@ -326,13 +326,27 @@ int run_dense(cdan_plan* p, ConvId first, int N, int h, int w, void* D, int ld, 
                   out_nchw ? 1 : 0);
 }
 
-int run_cbam(cdan_plan* p, int slot, const void* x, const void* mul, void* out, int N, int h, int w, cudaStream_t s) {
+int run_cbam(cdan_plan* p, int slot, const void* x, const void* mul, void* out, int N, int h, int w, bool pooled,
+             cudaStream_t s) {
   const CbamLayer& L = p->cbam[slot];
   CbamScratch sc;
   cbam_scratch_carve(p->buf.cbam_scratch, N, L.C, h, w, &sc);
   SpanGuard span(p, s, "cbam|C" + std::to_string(L.C));
-  CDAN_TRY(cbam_launch(p->dt, x, L.C, mul, L.C, out, L.C, N, h, w, L.C, L.w, sc, s));
-  p->launches += 5;
+  CDAN_TRY(cbam_launch(p->dt, x, L.C, mul, L.C, out, L.C, N, h, w, L.C, L.w, sc, pooled, s));
+  p->launches += pooled ? 4 : 5;
+  return 0;
+}
+
+// decoder stage glue (models/cdan.py:130,137-138,145-146): out = [up](a) + skip, with the following CBAM's pooling
+// partials written by the same kernel
+int run_up_add(cdan_plan* p, int cbam_slot, const void* a, int a_ld, const void* skip, int skip_ld, void* out, int N,
+               int oh, int ow, int up, cudaStream_t s) {
+  const int C = p->cbam[cbam_slot].C;
+  CbamScratch sc;
+  cbam_scratch_carve(p->buf.cbam_scratch, N, C, oh, ow, &sc);
+  SpanGuard span(p, s, "glue|up_add_C" + std::to_string(C));
+  CDAN_TRY(up_add_launch(p->dt, a, a_ld, skip, skip_ld, out, C, N, oh, ow, C, up, s, sc.psum, sc.pmax));
+  p->launches += 1;
   return 0;
 }
 
@@ -359,20 +373,20 @@ int forward_impl(cdan_plan* p, cudaStream_t s, const float* x, float* y, int N, 
   CDAN_TRY(run_dense(p, D3L0, N, H8, W8, b.D3, 320, 256, b.DN3, 256, s));
   CDAN_TRY(run_conv(p, ENC4, N, H8, W8, b.D3, 320, b.E4, 512, 0, s));
   // ---- bottleneck CBAM(512) (models/cdan.py:173)
-  CDAN_TRY(run_cbam(p, 0, b.E4, nullptr, b.B0, N, H8, W8, s));
+  CDAN_TRY(run_cbam(p, 0, b.E4, nullptr, b.B0, N, H8, W8, false, s));
   // ---- Decoder (models/cdan.py:126-159)
   CDAN_TRY(run_conv(p, DEC1, N, H8, W8, b.B0, 512, b.T1, 256, 0, s));
-  { SpanGuard span(p, s, "glue|up_add"); CDAN_TRY(up_add_launch(dt, b.T1, 256, b.D3, 320, b.A1, 256, N, H8, W8, 256, 0, s)); }
-  CDAN_TRY(run_cbam(p, 1, b.A1, b.DN3, b.C1, N, H8, W8, s));
+  CDAN_TRY(run_up_add(p, 1, b.T1, 256, b.D3, 320, b.A1, N, H8, W8, 0, s));
+  CDAN_TRY(run_cbam(p, 1, b.A1, b.DN3, b.C1, N, H8, W8, true, s));
   CDAN_TRY(run_conv(p, DEC2, N, H8, W8, b.C1, 256, b.T2, 128, 0, s));
-  { SpanGuard span(p, s, "glue|up_add"); CDAN_TRY(up_add_launch(dt, b.T2, 128, b.D2, 192, b.U2, 128, N, H4, W4, 128, 1, s)); }
-  CDAN_TRY(run_cbam(p, 2, b.U2, b.DN2, b.C2, N, H4, W4, s));
+  CDAN_TRY(run_up_add(p, 2, b.T2, 128, b.D2, 192, b.U2, N, H4, W4, 1, s));
+  CDAN_TRY(run_cbam(p, 2, b.U2, b.DN2, b.C2, N, H4, W4, true, s));
   CDAN_TRY(run_conv(p, DEC3, N, H4, W4, b.C2, 128, b.T3, 64, 0, s));
-  { SpanGuard span(p, s, "glue|up_add"); CDAN_TRY(up_add_launch(dt, b.T3, 64, b.D1, 128, b.U3, 64, N, H2, W2, 64, 1, s)); }
-  CDAN_TRY(run_cbam(p, 3, b.U3, b.DN1, b.C3, N, H2, W2, s));
+  CDAN_TRY(run_up_add(p, 3, b.T3, 64, b.D1, 128, b.U3, N, H2, W2, 1, s));
+  CDAN_TRY(run_cbam(p, 3, b.U3, b.DN1, b.C3, N, H2, W2, true, s));
   CDAN_TRY(run_conv(p, DEC4, N, H2, W2, b.C3, 64, b.T4, 8, 0, s));
-  { SpanGuard span(p, s, "glue|up_add"); CDAN_TRY(up_add_input_launch(dt, b.T4, 8, x, b.FD, 80, 16, N, H, W, s)); }
-  p->launches += 4;
+  { SpanGuard span(p, s, "glue|up_add_input"); CDAN_TRY(up_add_input_launch(dt, b.T4, 8, x, b.FD, 80, 16, N, H, W, s)); }
+  p->launches += 1;
   // final DenseBlock(3,3,16,4) + sigmoid, written straight to the caller's fp32 NCHW output
   CDAN_TRY(run_dense(p, FDL0, N, H, W, b.FD, 80, 16, nullptr, 3, s, y));
 

@@ -74,7 +74,7 @@ def test_per_stage_vs_oracle(cuda_device, dtype):
     plan = net.native_plan()
     # fp32: max error relative to the stage's magnitude; bf16: the same bound loosened to bf16 storage noise
     # accumulated through up to ~30 layers, plus a relative-RMS bound that a wrong kernel cannot meet
-    rel_max, rel_rms = (2e-5, 1e-5) if dtype == "fp32" else (0.12, 5e-2)
+    rel_max, rel_rms = (4e-5, 2e-5) if dtype == "fp32" else (0.12, 5e-2)
     for name, ref in expected_stages(st).items():
         got = plan.stage(name).cpu()
         assert got.shape == ref.shape, name
