@@ -38,9 +38,11 @@ namespace cdan {
 struct StreamPack {
   uint8_t* d_w = nullptr;   // fold / 1x1 image: [pass][chunk][s][NMMA rows][128 B swizzled]
   uint8_t* d_wk = nullptr;  // conv1 K-folded image: [192 rows][128 B swizzled] (only when Cin == 3, ks == 3, Cout <= 64)
+  uint8_t* d_ww = nullptr;  // wide 3x3 image (Cout 17..128, weights resident): [chunk][tap r*3+s][NTw rows][128 B swizzled]
   float* d_bias = nullptr;  // [npass * NT]
   int Cin = 0, Cout = 0, ks = 3, NT = 0, npass = 1, nchunks = 0;
-  size_t pass_bytes = 0;
+  int NTw = 0, npass_w = 1;
+  size_t pass_bytes = 0, wide_bytes = 0;
 };
 
 namespace {
@@ -65,6 +67,7 @@ struct SParams {
   int N, H, W, Cin;
   int pad;       // 1: 3x3, 0: 1x1
   int NT, NMMA;  // output channels per accumulator row / MMA N
+  int wide;      // 3x3 with NT > 16: nine separate taps (3 ring slots x 3 shifted views), no shadow slots
   int SW;        // TMEM columns per ring slot (= NT, or 3*NT when the horizontal taps are folded into N as well)
   int R;         // ring slots (excluding the two shadow slots)
   int TW, strips, SEG, segs, nitems;
@@ -129,12 +132,15 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int PAD = FOLD == 3 ? 1 : 0;
+  // FOLD: 1 = 1x1 conv; 3 = 3x3 in the input mode's default form (kSPro: nine-tap fold + shift epilogue, kSNchw: conv1
+  // K-fold, kSTma: wide nine-tap); 9 = 3x3 TMA-fed with the nine-tap fold (16-channel outputs, e.g. decoder.conv4)
+  constexpr int PAD = FOLD != 1 ? 1 : 0;
   constexpr int kEpiWarps = epi_warps(IN), kWorkWarp0 = kEpiWarp0 + kEpiWarps, kWorkWarps = work_warps(IN);
   constexpr int kEG = kEpiWarps / 4;  // epilogue groups
   // SHIFT: all nine taps folded into N (N = 9*NT); lane l of warp-quarter q holds strip pixel 30*q + l - 1, the
   // epilogue adds the three horizontal-tap column groups of lanes l-1, l, l+1 (valid outputs: l = 1..30).
-  constexpr bool SHIFT = FOLD == 3 && IN != kSNchw;
+  constexpr bool SHIFT = (FOLD == 3 && IN == kSPro) || FOLD == 9;
+  constexpr bool WIDE = FOLD == 3 && IN == kSTma;
   constexpr bool RELU = IN != kSPro;  // dense-block layers have no output ReLU; ConvBlock / decoder convs always do
 
   if (tid == 0) {
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
-  if (FOLD == 3 && warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {  // ring accumulators start at zero
+  if (PAD && warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {  // ring accumulators start at zero
     const uint32_t lb = tmem_base + (uint32_t((warp & 3) * 32) << 16);
     for (int c = 0; c < 512; c += 16) ptx::tmem_st16_zero(lb + c);
     ptx::tmem_wait_st();
@@ -183,8 +189,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
   if (warp == 0) {
     // ============================================================ producer: resident weights, then A rows via TMA.
     // The whole warp walks the loop (uniform control flow); the copies are issued by the elected lane only.
-    const uint32_t leader = ptx::elect_one() ? 1u : 0u;
-    if (leader) {
+    if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(&w_full, P.wbytes);
       for (uint32_t off = 0; off < P.wbytes; off += 32768)
         ptx::bulk_g2s(sW + off, P.wpack + off, min(32768u, P.wbytes - off), &w_full);
@@ -197,8 +202,11 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
         const int j0 = max(it.h0 - 1, 0), j1 = min(it.h1 + 1, P.H);
         for (int j = j0; j < j1; ++j) {
           ptx::mbar_wait(&raw_empty[rr.i], (rr.w & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx_if(leader, &raw_full[rr.i], kRawW * 3 * 4);
-          ptx::tma_load_4d_if(leader, s_raw + rr.i * kRawFloats, &tmapA, it.w0 - 4, j, 0, it.n, &raw_full[rr.i]);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&raw_full[rr.i], kRawW * 3 * 4);
+            ptx::tma_load_4d(s_raw + rr.i * kRawFloats, &tmapA, it.w0 - 4, j, 0, it.n, &raw_full[rr.i]);
+          }
+          __syncwarp();
           rr.step(kRawStages);
         }
       }
@@ -212,15 +220,17 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
             // kSTma: the row feeds the MMA directly; kSPro: it lands raw and the workers activate it in place
             uint64_t* full = IN == kSTma ? &a_full[st.i] : &raw_full[st.i];
             ptx::mbar_wait(&a_empty[st.i], (st.w & 1) ^ 1);
-            ptx::mbar_arrive_expect_tx_if(leader, full, kStage);
-            uint8_t* dst = sA + size_t(st.i) * kStage;
-            if (SHIFT) {
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(full, kStage);
+              uint8_t* dst = sA + size_t(st.i) * kStage;
+              if (SHIFT) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                ptx::tma_load_4d_if(leader, dst + q * 4096, &tmapA, c * 64, it.w0 - 1 + 30 * q, j, it.n, full);
-            } else {
-              ptx::tma_load_4d_if(leader, dst, &tmapA, c * 64, it.w0, j, it.n, full);
+                for (int q = 0; q < 4; ++q) ptx::tma_load_4d(dst + q * 4096, &tmapA, c * 64, it.w0 - 1 + 30 * q, j, it.n, full);
+              } else {
+                ptx::tma_load_4d(dst, &tmapA, c * 64, it.w0 - (WIDE ? 1 : 0), j, it.n, full);
+              }
             }
+            __syncwarp();
             st.step(P.SA);
           }
         }
@@ -229,7 +239,6 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
   } else if (warp == 1) {
     // ============================================================ MMA issuer: uniform loop, elected lane issues
     {
-      const uint32_t leader = ptx::elect_one() ? 1u : 0u;
       const uint32_t idesc = ptx::umma_idesc_bf16(128, P.NMMA);
       const uint64_t desc_hi = ptx::umma_desc_sw128(0, 1024) & 0xffffffff00000000ull;
       const uint32_t flags = uint32_t(ptx::umma_desc_sw128(0, 1024) & 0xffffffffull);
@@ -257,25 +266,51 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
               ptx::mbar_wait(&a_full[st.i], st.w & 1);
               ptx::tc_fence_after_sync();
               const uint32_t a0 = a_base + uint32_t(st.i) * (kStage >> 4);
-              const uint32_t acc0 = FOLD == 3 ? 1u : (c != 0 ? 1u : 0u);
+              const uint32_t acc0 = PAD ? 1u : (c != 0 ? 1u : 0u);
+              // One elected lane issues (ptxas keeps descriptors in uniform registers inside an elect.sync region;
+              // a per-thread predicate on the instruction instead costs a vote + R2UR.BROADCAST sequence per MMA).
+              if (ptx::elect_one()) {
+                if (WIDE) {
+                  // nine taps: kernel row r feeds accumulator row G + (2 - r) (its own ring slot), the horizontal tap
+                  // s is the A view shifted by s pixels; weight blocks are ordered [r*3+s]
 #pragma unroll
-              for (int k = 0; k < (IN == kSNchw ? 1 : 4); ++k)
-                if (k < ksteps)
-                  ptx::umma_bf16_if(leader, dcol, desc_hi | (a0 + uint32_t(2 * k)), desc_hi | (b0 + uint32_t(2 * k)), idesc,
-                                    k == 0 ? acc0 : 1u);
-              ptx::umma_commit_if(leader, &a_empty[st.i]);
+                  for (int pos = 0; pos < 3; ++pos) {
+                    int sl = dr.i + pos;
+                    if (sl >= P.R) sl -= P.R;
+                    const uint32_t dc = tmem_base + uint32_t(sl * P.SW);
+#pragma unroll
+                    for (int s = 0; s < 3; ++s) {
+                      const uint32_t bb = b0 + uint32_t((2 - pos) * 3 + s) * blk16;
+#pragma unroll
+                      for (int k = 0; k < 4; ++k)
+                        if (k < ksteps)
+                          ptx::umma_bf16(dc, desc_hi | (a0 + uint32_t(8 * s + 2 * k)), desc_hi | (bb + uint32_t(2 * k)), idesc, 1u);
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < (IN == kSNchw ? 1 : 4); ++k)
+                    if (k < ksteps)
+                      ptx::umma_bf16(dcol, desc_hi | (a0 + uint32_t(2 * k)), desc_hi | (b0 + uint32_t(2 * k)), idesc, k == 0 ? acc0 : 1u);
+                }
+                ptx::umma_commit(&a_empty[st.i]);
+              }
+              __syncwarp();
               st.step(P.SA);
-              b0 += blk16;
+              b0 += WIDE ? 9u * blk16 : blk16;
             }
           }
-          ptx::umma_commit_if(leader, &acc_done[dr.i]);
+          if (ptx::elect_one()) ptx::umma_commit(&acc_done[dr.i]);
+          __syncwarp();
           dr.step(P.R);
           fr.step(P.R);
         }
         if (PAD) {  // the two trailing accumulator rows of the segment receive no further input
-          ptx::umma_commit_if(leader, &acc_done[dr.i]);
+          if (ptx::elect_one()) ptx::umma_commit(&acc_done[dr.i]);
+          __syncwarp();
           dr.step(P.R);
-          ptx::umma_commit_if(leader, &acc_done[dr.i]);
+          if (ptx::elect_one()) ptx::umma_commit(&acc_done[dr.i]);
+          __syncwarp();
           dr.step(P.R);
           fr.add(2, P.R);
         }
@@ -309,7 +344,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
           ptx::mbar_wait(&acc_done[slot], sr.w & 1);
           ptx::tc_fence_after_sync();
           const bool row_ok = i >= it.h0 && i < it.h1;
-          const bool shadow = FOLD == 3 && slot < 2;
+          const bool shadow = PAD && !WIDE && slot < 2;
           const uint32_t tm = lb + uint32_t(slot * P.SW), ts = lb + uint32_t((P.R + slot) * P.SW);
           // 8 output channels at a time keeps the live register set small (spills are L2 round trips here: with
           // ~224 KB of shared memory in use the L1 has almost no capacity left)
@@ -361,7 +396,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
                   ptx::tmem_wait_ld();
                 }
               }
-              if (FOLD == 3) {
+              if (PAD) {
                 ptx::tmem_st8_zero(tm + c0);
                 if (shadow) ptx::tmem_st8_zero(ts + c0);
               }
@@ -387,7 +422,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
               }
             }
           }
-          if (FOLD == 3) ptx::tmem_wait_st();
+          if (PAD) ptx::tmem_wait_st();
           ptx::tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&acc_free[slot]);
@@ -408,7 +443,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
           ptx::mbar_wait(&acc_done[sl1], sr.w & 1);
           ptx::tc_fence_after_sync();
           const bool row_ok = i >= it.h0 && i < it.h1;
-          const bool sh0 = sl0 < 2, sh1 = sl1 < 2;
+          const bool sh0 = !WIDE && sl0 < 2, sh1 = !WIDE && sl1 < 2;
           const uint32_t t0 = lb + uint32_t(sl0 * P.NT), t1 = lb + uint32_t(sl1 * P.NT);
           const uint32_t ts0 = lb + uint32_t((P.R + sl0) * P.NT), ts1 = lb + uint32_t((P.R + sl1) * P.NT);
           bf16* o_row = P.out + ((size_t(it.n) * (P.H >> 1) + (i >> 1)) * (P.W >> 1) + (col >> 1)) * P.out_ld;
@@ -645,7 +680,6 @@ int stream_pack_create(const float* w, const float* bias, int Cin, int Cout, int
               }
             }
       }
-    for (int co = 0; co < Cout; ++co) hb[co] = bias[co];
     if (cudaMalloc(&p->d_w, img.size()) != cudaSuccess ||
         cudaMemcpy(p->d_w, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
       stream_pack_destroy(p);
@@ -659,18 +693,42 @@ int stream_pack_create(const float* w, const float* bias, int Cin, int Cout, int
         for (int s = 0; s < 3; ++s)
           for (int ci = 0; ci < 3; ++ci)
             put_bf16(k.data(), pos * 64 + co, s * 3 + ci, w[(size_t((2 - pos) * 3 + s) * Cin + ci) * CoutP + co]);
-    if (hb.empty()) {
-      hb.assign(64, 0.f);
-      for (int co = 0; co < Cout; ++co) hb[co] = bias[co];
-    }
     if (cudaMalloc(&p->d_wk, k.size()) != cudaSuccess ||
         cudaMemcpy(p->d_wk, k.data(), k.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
       stream_pack_destroy(p);
       return fail("stream_pack: weight upload failed");
     }
   }
-  if (!hb.empty()) {
-    hb.resize(std::max<size_t>(hb.size(), 64), 0.f);
+  if (ks == 3) {  // wide form: per 64-channel pass nine [NTw x 64ch] blocks per K-chunk, resident in shared memory
+    const int NTw = Cout <= 16 ? 16 : 64, npw = (Cout + NTw - 1) / NTw;
+    const size_t block = size_t(NTw) * 128, bytes = size_t(p->nchunks) * 9 * block;
+    if (bytes <= 152 * 1024 && npw <= 2) {
+      std::vector<uint8_t> ww(bytes * npw, 0);
+      for (int pass = 0; pass < npw; ++pass)
+        for (int c = 0; c < p->nchunks; ++c)
+          for (int tap = 0; tap < 9; ++tap)
+            for (int nn = 0; nn < NTw; ++nn) {
+              const int co = pass * NTw + nn;
+              if (co >= Cout) continue;
+              for (int k = 0; k < 64; ++k) {
+                const int ci = c * 64 + k;
+                if (ci >= Cin) continue;
+                put_bf16(ww.data() + pass * bytes + (size_t(c) * 9 + tap) * block, nn, k, w[(size_t(tap) * Cin + ci) * CoutP + co]);
+              }
+            }
+      p->NTw = NTw;
+      p->npass_w = npw;
+      p->wide_bytes = bytes;
+      if (cudaMalloc(&p->d_ww, ww.size()) != cudaSuccess ||
+          cudaMemcpy(p->d_ww, ww.data(), ww.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        stream_pack_destroy(p);
+        return fail("stream_pack: weight upload failed");
+      }
+    }
+  }
+  {
+    hb.assign(std::max<size_t>(std::max<size_t>(128, size_t(Cout)), size_t(p->npass) * std::max(p->NT, 1)), 0.f);
+    for (int co = 0; co < Cout; ++co) hb[co] = bias[co];
     if (cudaMalloc(&p->d_bias, hb.size() * 4) != cudaSuccess ||
         cudaMemcpy(p->d_bias, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
       stream_pack_destroy(p);
@@ -685,15 +743,21 @@ void stream_pack_destroy(StreamPack* p) {
   if (!p) return;
   if (p->d_w) cudaFree(p->d_w);
   if (p->d_wk) cudaFree(p->d_wk);
+  if (p->d_ww) cudaFree(p->d_ww);
   if (p->d_bias) cudaFree(p->d_bias);
   delete p;
 }
 
 bool conv_stream_supported(const ConvDesc& d, const StreamPack& pk) {
   if (d.in_nchw) return pk.d_wk && d.Cin == 3 && d.W % 4 == 0 && d.relu && !d.pre_scale && !d.out_nchw && d.out_ld % 8 == 0 && (!d.pool || !((d.H | d.W) & 1));
-  if (!pk.d_w || pk.NT == 0) return false;
+  if (d.Cin % 8 != 0 || d.in_ld % 8 != 0) return false;
   if ((d.relu != 0) != (d.pre_scale == nullptr)) return false;  // ReLU is compiled in per input mode
-  if (d.Cin % 8 != 0 || d.in_ld % 8 != 0 || d.pool) return false;
+  if (d.ks == 3 && !d.pre_scale) {  // TMA-fed 3x3: nine-tap fold for 16-wide outputs, else wide form (weights resident)
+    if (d.out_nchw || d.out_ld % 8 != 0) return false;
+    if (pk.d_w && pk.NT == 16 && !d.pool) return true;
+    return pk.d_ww && (!d.pool || !((d.H | d.W) & 1));
+  }
+  if (!pk.d_w || pk.NT == 0 || d.pool) return false;
   if (d.out_nchw) return d.Cout <= 16;
   return d.out_ld % 8 == 0;
 }
@@ -710,14 +774,17 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   SParams P{};
   P.N = d.N; P.H = d.H; P.W = d.W; P.Cin = d.Cin;
   P.pad = fold == 3 ? 1 : 0;
-  P.NT = kfold ? 64 : pk.NT;
-  const bool shift = fold == 3 && !kfold;
-  P.NMMA = shift ? 9 * P.NT : fold * P.NT;
+  const bool fold9 = fold == 3 && in_mode == kSTma && pk.d_w && pk.NT == 16 && !d.pool;  // TMA-fed, 16-wide: nine-tap fold
+  const bool wide = fold == 3 && in_mode == kSTma && !fold9;
+  P.wide = wide ? 1 : 0;
+  P.NT = kfold ? 64 : (wide ? pk.NTw : pk.NT);
+  const bool shift = (fold == 3 && in_mode == kSPro) || fold9;
+  P.NMMA = shift ? 9 * P.NT : (wide ? P.NT : fold * P.NT);
   P.SW = shift ? 3 * P.NT : P.NT;
-  P.R = fold == 3 ? std::min(30, 512 / P.SW - 2) : std::min(kMaxR, 512 / P.NT);
+  P.R = (fold == 3 && !wide) ? std::min(30, 512 / P.SW - 2) : std::min(kMaxR, 512 / P.NT);
   P.nchunks = kfold ? 1 : pk.nchunks;
   P.nS = 1;
-  const int tw_max = shift ? 120 : 128;
+  const int tw_max = shift ? 120 : (wide ? 126 : 128);
   P.strips = ceil_div(d.W, tw_max);
   P.TW = std::min(tw_max, kfold ? (ceil_div(d.W, P.strips) + 3) & ~3 : (ceil_div(d.W, P.strips) + 1) & ~1);
   const int want_segs = std::max(1, ceil_div(sms * 8, d.N * P.strips));
@@ -728,7 +795,7 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   P.in = reinterpret_cast<const bf16*>(d.in); P.in_ld = d.in_ld;
   P.in_nchw = d.in_nchw; P.pre_s = d.pre_scale; P.pre_t = d.pre_shift;
   P.out_ld = d.out_ld; P.out_nchw = d.out_nchw;
-  P.wbytes = uint32_t(kfold ? size_t(192) * 128 : pk.pass_bytes);
+  P.wbytes = uint32_t(kfold ? size_t(192) * 128 : (wide ? pk.wide_bytes : pk.pass_bytes));
   const int tail = 2 * P.nchunks * 64 * 4 + std::max(P.NT, 64) * 4 + 256 + (kfold ? kRawStages * kRawFloats * 4 + 128 : 0);
   P.SA = std::min(kMaxSA, (kSmemLimit - 1024 - int(P.wbytes) - tail) / kStage);
   if (P.SA < 3) return fail("conv_stream: weights leave no room for the activation pipeline");
@@ -766,9 +833,9 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   }
   const int grid = std::min(P.nitems, sms);
   const int threads = 32 * (kEpiWarp0 + epi_warps(in_mode) + work_warps(in_mode));
-  const int npass = kfold ? 1 : pk.npass;
+  const int npass = kfold ? 1 : (wide ? pk.npass_w : pk.npass);
   for (int pass = 0; pass < npass; ++pass) {
-    P.wpack = kfold ? pk.d_wk : pk.d_w + size_t(pass) * pk.pass_bytes;
+    P.wpack = kfold ? pk.d_wk : (wide ? pk.d_ww + size_t(pass) * pk.wide_bytes : pk.d_w + size_t(pass) * pk.pass_bytes);
     P.bias = pk.d_bias + size_t(pass) * P.NT;
     P.Cout = std::min(P.NT, d.Cout - pass * P.NT);
     P.out = reinterpret_cast<bf16*>(d.out) + size_t(pass) * P.NT;
@@ -782,7 +849,9 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
     if (kfold) rc = d.pool ? launch(conv_stream_kernel<kSNchw, 3, kSPool>) : launch(conv_stream_kernel<kSNchw, 3, kSStore>);
     else if (fold == 3) {
       if (d.out_nchw) rc = in_mode == kSPro ? launch(conv_stream_kernel<kSPro, 3, kSNchwOut>) : launch(conv_stream_kernel<kSTma, 3, kSNchwOut>);
-      else rc = in_mode == kSPro ? launch(conv_stream_kernel<kSPro, 3, kSStore>) : launch(conv_stream_kernel<kSTma, 3, kSStore>);
+      else if (in_mode == kSPro) rc = launch(conv_stream_kernel<kSPro, 3, kSStore>);
+      else if (fold9) rc = launch(conv_stream_kernel<kSTma, 9, kSStore>);
+      else rc = d.pool ? launch(conv_stream_kernel<kSTma, 3, kSPool>) : launch(conv_stream_kernel<kSTma, 3, kSStore>);
     } else {
       if (d.out_nchw) rc = in_mode == kSPro ? launch(conv_stream_kernel<kSPro, 1, kSNchwOut>) : launch(conv_stream_kernel<kSTma, 1, kSNchwOut>);
       else rc = in_mode == kSPro ? launch(conv_stream_kernel<kSPro, 1, kSStore>) : launch(conv_stream_kernel<kSTma, 1, kSStore>);
