@@ -50,7 +50,8 @@ CDAN_API int cdan_plan_destroy(cdan_plan* plan);
 CDAN_API int cdan_plan_load_weights(cdan_plan* plan, int n, const char* const* keys, const void* const* ptrs,
                            const int64_t* numels);
 
-/* Options: "conv_impl" = 0 auto (tcgen05 where supported), 1 force CUDA-core path;
+/* Options: "host_chunk" = images per step of cdan_forward_host's copy/compute pipeline (default 8);
+ *          "conv_impl" = 0 auto (tcgen05 where supported), 1 force CUDA-core path;
  *          "profile"   = 1 brackets every launch group with CUDA events on the launching stream. */
 CDAN_API int cdan_plan_set_option(cdan_plan* plan, const char* name, int value);
 
@@ -60,7 +61,9 @@ CDAN_API int cdan_workspace_bytes(cdan_plan* plan, int N, int H, int W, size_t* 
 /* CDAN.forward in eval mode (reference models/cdan.py:171-176).  x, y: fp32 NCHW contiguous [N,3,H,W] on the plan's
  * device.  H % 8 != 0 or W % 8 != 0 is an error (the reference fails with a size mismatch there too). */
 CDAN_API int cdan_forward(cdan_plan* plan, void* stream, const float* x, float* y, int N, int H, int W);
-/* Same through HOST buffers: H2D copy of x, forward, D2H copy of y, then a stream synchronise. */
+/* Same through HOST buffers (pinned memory recommended): the batch is processed in sub-batches of "host_chunk" images;
+ * the H2D copy of the next and the D2H copy of the previous sub-batch overlap the forward of the current one on
+ * separate streams.  Returns after the last D2H copy has completed. */
 CDAN_API int cdan_forward_host(cdan_plan* plan, const float* x_host, float* y_host, int N, int H, int W);
 
 /* Read an intermediate tensor of the most recent cdan_forward as fp32 NCHW (per-stage parity tests).

@@ -2,6 +2,7 @@
 #include "plan.hpp"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/cdan_b200.h"
@@ -242,8 +243,6 @@ size_t carve(Buffers& b, char* base, DType dt, int N, int H, int W) {
   sc = std::max(sc, cbam_scratch_floats(N, 128, H / 4, W / 4));
   sc = std::max(sc, cbam_scratch_floats(N, 64, H / 2, W / 2));
   b.cbam_scratch = (float*)take(sc * sizeof(float));
-  b.x_dev = (float*)take(p1 * 3 * sizeof(float));
-  b.y_dev = (float*)take(p1 * 3 * sizeof(float));
   b.total_bytes = off;
   return off;
 }
@@ -305,6 +304,11 @@ int run_conv(cdan_plan* p, ConvId id, int N, int H, int W, const void* in, int i
   const bool umma = p->dt == kBF16 && p->conv_impl == 0 && L.umma && conv_umma_supported(d);
   SpanGuard span(p, s, std::string("conv|") + L.name + (umma ? (d.pre_scale || d.in_nchw ? "|umma_pro" : "|umma_tma") : "|simt"));
   CDAN_TRY(conv_dispatch(p, L, d, s));
+  static const bool debug_sync = getenv("CDAN_DEBUG_SYNC") != nullptr;
+  if (debug_sync) {
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return fail("kernel of layer '" + L.name + "' failed: " + cudaGetErrorString(e));
+  }
   p->launches += 1;
   return 0;
 }
@@ -448,6 +452,14 @@ int cdan_plan_destroy(cdan_plan* p) {
   free_weights(p);
   if (p->ws) cudaFree(p->ws);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
+  if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
+  if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (p->ev_h2d[i]) cudaEventDestroy(p->ev_h2d[i]);
+    if (p->ev_comp[i]) cudaEventDestroy(p->ev_comp[i]);
+    if (p->ev_d2h[i]) cudaEventDestroy(p->ev_d2h[i]);
+  }
+  if (p->host_stage) cudaFree(p->host_stage);
   delete p;
   return 0;
 }
@@ -456,6 +468,11 @@ int cdan_plan_set_option(cdan_plan* p, const char* name, int value) {
   if (!p || !name) return fail("cdan_plan_set_option: NULL argument");
   if (!strcmp(name, "profile")) {
     p->profile = value ? 1 : 0;
+    return 0;
+  }
+  if (!strcmp(name, "host_chunk")) {
+    if (value < 1) return fail("host_chunk must be >= 1");
+    p->host_chunk = value;
     return 0;
   }
   if (!strcmp(name, "conv_impl")) {
@@ -520,13 +537,47 @@ int cdan_forward_host(cdan_plan* p, const float* x_host, float* y_host, int N, i
   if (!p || !x_host || !y_host) return fail("cdan_forward_host: NULL argument");
   DeviceGuard g(p->device);
   if (H % 8 || W % 8 || N <= 0) return fail("cdan_forward_host: H and W must be multiples of 8");
-  if (!p->own_stream) CDAN_CUDA_OK(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
-  CDAN_TRY(ensure_workspace(p, N, H, W));
-  const size_t bytes = size_t(N) * 3 * H * W * sizeof(float);
-  CDAN_CUDA_OK(cudaMemcpyAsync(p->buf.x_dev, x_host, bytes, cudaMemcpyHostToDevice, p->own_stream));
-  CDAN_TRY(forward_impl(p, p->own_stream, p->buf.x_dev, p->buf.y_dev, N, H, W));
-  CDAN_CUDA_OK(cudaMemcpyAsync(y_host, p->buf.y_dev, bytes, cudaMemcpyDeviceToHost, p->own_stream));
-  CDAN_CUDA_OK(cudaStreamSynchronize(p->own_stream));
+  // Sub-batch pipeline over three streams: the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the forward
+  // of chunk k (PCIe is full duplex), with double-buffered device staging.
+  if (!p->own_stream) {
+    CDAN_CUDA_OK(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+    CDAN_CUDA_OK(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
+    CDAN_CUDA_OK(cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CDAN_CUDA_OK(cudaEventCreateWithFlags(&p->ev_h2d[i], cudaEventDisableTiming));
+      CDAN_CUDA_OK(cudaEventCreateWithFlags(&p->ev_comp[i], cudaEventDisableTiming));
+      CDAN_CUDA_OK(cudaEventCreateWithFlags(&p->ev_d2h[i], cudaEventDisableTiming));
+    }
+  }
+  const int cb = std::max(1, std::min(N, p->host_chunk));
+  const size_t img_floats = size_t(3) * H * W, slot_floats = size_t(cb) * img_floats;
+  if (p->host_stage_bytes < 4 * slot_floats * sizeof(float)) {
+    CDAN_CUDA_OK(cudaDeviceSynchronize());
+    if (p->host_stage) CDAN_CUDA_OK(cudaFree(p->host_stage));
+    p->host_stage = nullptr;
+    p->host_stage_bytes = 0;
+    CDAN_CUDA_OK(cudaMalloc(&p->host_stage, 4 * slot_floats * sizeof(float)));
+    p->host_stage_bytes = 4 * slot_floats * sizeof(float);
+  }
+  CDAN_TRY(ensure_workspace(p, cb, H, W));
+  int k = 0;
+  for (int n0 = 0; n0 < N; n0 += cb, ++k) {
+    const int nb = std::min(cb, N - n0), slot = k & 1;
+    float* xs = p->host_stage + size_t(slot) * 2 * slot_floats;
+    float* ys = xs + slot_floats;
+    const size_t bytes = size_t(nb) * img_floats * sizeof(float);
+    if (k >= 2) CDAN_CUDA_OK(cudaStreamWaitEvent(p->h2d_stream, p->ev_comp[slot], 0));  // x slot free again
+    CDAN_CUDA_OK(cudaMemcpyAsync(xs, x_host + size_t(n0) * img_floats, bytes, cudaMemcpyHostToDevice, p->h2d_stream));
+    CDAN_CUDA_OK(cudaEventRecord(p->ev_h2d[slot], p->h2d_stream));
+    CDAN_CUDA_OK(cudaStreamWaitEvent(p->own_stream, p->ev_h2d[slot], 0));
+    if (k >= 2) CDAN_CUDA_OK(cudaStreamWaitEvent(p->own_stream, p->ev_d2h[slot], 0));      // y slot drained
+    CDAN_TRY(forward_impl(p, p->own_stream, xs, ys, nb, H, W));
+    CDAN_CUDA_OK(cudaEventRecord(p->ev_comp[slot], p->own_stream));
+    CDAN_CUDA_OK(cudaStreamWaitEvent(p->d2h_stream, p->ev_comp[slot], 0));
+    CDAN_CUDA_OK(cudaMemcpyAsync(y_host + size_t(n0) * img_floats, ys, bytes, cudaMemcpyDeviceToHost, p->d2h_stream));
+    CDAN_CUDA_OK(cudaEventRecord(p->ev_d2h[slot], p->d2h_stream));
+  }
+  CDAN_CUDA_OK(cudaStreamSynchronize(p->d2h_stream));
   return 0;
 }
 

@@ -50,7 +50,6 @@ struct Buffers {
   // all NHWC in the plan's storage type; names follow the reference's forward (models/cdan.py:70-98,126-159)
   void *D1, *DN1, *D2, *DN2, *D3, *DN3, *E4, *B0, *T1, *A1, *C1, *T2, *U2, *C2, *T3, *U3, *C3, *T4, *FD;
   float* cbam_scratch;
-  float *x_dev, *y_dev;  // staging for the host-buffer entry point
   size_t total_bytes;
 };
 
@@ -71,6 +70,12 @@ struct cdan_plan {
   cdan::Buffers buf{};
   std::map<std::string, cdan::Stage> stages;
   cudaStream_t own_stream = nullptr;
+  // host-buffer entry point: copy streams, per-slot events and double-buffered device staging (sub-batch pipeline)
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  float* host_stage = nullptr;  // [2 slots][x | y]
+  size_t host_stage_bytes = 0;
+  int host_chunk = 8;           // images per pipeline step (option "host_chunk")
   // optional per-launch CUDA-event timing ("profile" option): label -> accumulated ms / count
   int profile = 0;
   struct Span { std::string label; cudaEvent_t e0, e1; };
