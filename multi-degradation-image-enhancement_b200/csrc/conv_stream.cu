@@ -38,11 +38,12 @@ namespace cdan {
 struct StreamPack {
   uint8_t* d_w = nullptr;   // fold / 1x1 image: [pass][chunk][s][NMMA rows][128 B swizzled]
   uint8_t* d_wk = nullptr;  // conv1 K-folded image: [192 rows][128 B swizzled] (only when Cin == 3, ks == 3, Cout <= 64)
+  uint8_t* d_wr = nullptr;  // 16-wide 3x3, row-fold form: [chunk][s][48 rows = pos*16+co][128 B swizzled]
   uint8_t* d_ww = nullptr;  // wide 3x3 image (Cout 17..128, weights resident): [chunk][tap r*3+s][NTw rows][128 B swizzled]
   float* d_bias = nullptr;  // [npass * NT]
   int Cin = 0, Cout = 0, ks = 3, NT = 0, npass = 1, nchunks = 0;
   int NTw = 0, npass_w = 1;
-  size_t pass_bytes = 0, wide_bytes = 0;
+  size_t pass_bytes = 0, wide_bytes = 0, rfold_bytes = 0;
 };
 
 namespace {
@@ -84,7 +85,14 @@ struct SParams {
   bf16* out;
   int out_ld;
   float* out_nchw;
+  unsigned long long* trace;  // timeline of CTA 0 (debug builds with -DCDAN_STREAM_TRACE_BUILD): [role][kTraceN]
 };
+constexpr int kTraceN = 256;
+#ifdef CDAN_STREAM_TRACE_BUILD
+#define STRACE(role, idx) do { if (P.trace && blockIdx.x == 0 && (idx) < kTraceN) P.trace[(role) * kTraceN + (idx)] = clock64(); } while (0)
+#else
+#define STRACE(role, idx) do { } while (0)
+#endif
 
 struct Item {
   int n, w0, h0, h1;
@@ -134,7 +142,9 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // FOLD: 1 = 1x1 conv; 3 = 3x3 in the input mode's default form (kSPro: nine-tap fold + shift epilogue, kSNchw: conv1
   // K-fold, kSTma: wide nine-tap); 9 = 3x3 TMA-fed with the nine-tap fold (16-channel outputs, e.g. decoder.conv4)
+  //       4 = 3x3 with only the vertical taps folded into N (N = 3*NT) and the horizontal taps as shifted A views
   constexpr int PAD = FOLD != 1 ? 1 : 0;
+  constexpr bool RFOLD = FOLD == 4;
   constexpr int kEpiWarps = epi_warps(IN), kWorkWarp0 = kEpiWarp0 + kEpiWarps, kWorkWarps = work_warps(IN);
   constexpr int kEG = kEpiWarps / 4;  // epilogue groups
   // SHIFT: all nine taps folded into N (N = 9*NT); lane l of warp-quarter q holds strip pixel 30*q + l - 1, the
@@ -220,6 +230,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
             // kSTma: the row feeds the MMA directly; kSPro: it lands raw and the workers activate it in place
             uint64_t* full = IN == kSTma ? &a_full[st.i] : &raw_full[st.i];
             ptx::mbar_wait(&a_empty[st.i], (st.w & 1) ^ 1);
+            if (lane == 0) STRACE(0, st.w * P.SA + st.i);
             if (ptx::elect_one()) {
               ptx::mbar_arrive_expect_tx(full, kStage);
               uint8_t* dst = sA + size_t(st.i) * kStage;
@@ -227,7 +238,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
 #pragma unroll
                 for (int q = 0; q < 4; ++q) ptx::tma_load_4d(dst + q * 4096, &tmapA, c * 64, it.w0 - 1 + 30 * q, j, it.n, full);
               } else {
-                ptx::tma_load_4d(dst, &tmapA, c * 64, it.w0 - (WIDE ? 1 : 0), j, it.n, full);
+                ptx::tma_load_4d(dst, &tmapA, c * 64, it.w0 - ((WIDE || RFOLD) ? 1 : 0), j, it.n, full);
               }
             }
             __syncwarp();
@@ -258,6 +269,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
           const int j = it.h0 - PAD + jj;
           if (fr.w > 0) ptx::mbar_wait(&acc_free[fr.i], (fr.w - 1) & 1);
           ptx::tc_fence_after_sync();
+          if (lane == 0) STRACE(7, dr.w * P.R + dr.i);
           if (j >= 0 && j < P.H) {
             const uint32_t dcol = tmem_base + uint32_t(dr.i * P.SW);
             uint32_t b0 = b_base;
@@ -265,6 +277,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
               const int ksteps = c == P.nchunks - 1 ? klast : 4;
               ptx::mbar_wait(&a_full[st.i], st.w & 1);
               ptx::tc_fence_after_sync();
+              if (lane == 0) STRACE(3, st.w * P.SA + st.i);
               const uint32_t a0 = a_base + uint32_t(st.i) * (kStage >> 4);
               const uint32_t acc0 = PAD ? 1u : (c != 0 ? 1u : 0u);
               // One elected lane issues (ptxas keeps descriptors in uniform registers inside an elect.sync region;
@@ -287,6 +300,13 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
                           ptx::umma_bf16(dc, desc_hi | (a0 + uint32_t(8 * s + 2 * k)), desc_hi | (bb + uint32_t(2 * k)), idesc, 1u);
                     }
                   }
+                } else if (RFOLD) {
+#pragma unroll
+                  for (int s = 0; s < 3; ++s)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      if (k < ksteps)
+                        ptx::umma_bf16(dcol, desc_hi | (a0 + uint32_t(8 * s + 2 * k)), desc_hi | (b0 + uint32_t(s) * blk16 + uint32_t(2 * k)), idesc, 1u);
                 } else {
 #pragma unroll
                   for (int k = 0; k < (IN == kSNchw ? 1 : 4); ++k)
@@ -295,9 +315,10 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
                 }
                 ptx::umma_commit(&a_empty[st.i]);
               }
+              if (lane == 0) STRACE(4, st.w * P.SA + st.i);
               __syncwarp();
               st.step(P.SA);
-              b0 += WIDE ? 9u * blk16 : blk16;
+              b0 += WIDE ? 9u * blk16 : (RFOLD ? 3u * blk16 : blk16);
             }
           }
           if (ptx::elect_one()) ptx::umma_commit(&acc_done[dr.i]);
@@ -343,6 +364,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
           const int slot = sr.i;
           ptx::mbar_wait(&acc_done[slot], sr.w & 1);
           ptx::tc_fence_after_sync();
+          if (q == 0 && lane == 0) STRACE(5, sr.w * P.R + sr.i);
           const bool row_ok = i >= it.h0 && i < it.h1;
           const bool shadow = PAD && !WIDE && slot < 2;
           const uint32_t tm = lb + uint32_t(slot * P.SW), ts = lb + uint32_t((P.R + slot) * P.SW);
@@ -426,6 +448,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
           ptx::tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&acc_free[slot]);
+          if (q == 0 && lane == 0) STRACE(6, sr.w * P.R + sr.i);
           sr.add(kEG, P.R);
           i += kEG;
           if (EPI == kSNchwOut) o_f += kEG * row_elems; else o_b += kEG * row_elems;
@@ -534,7 +557,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
         bool ok[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int col = SHIFT ? it.w0 - 1 + 30 * i + qb : it.w0 + qb + 32 * i;
+          const int col = SHIFT ? it.w0 - 1 + 30 * i + qb : it.w0 - (RFOLD ? 1 : 0) + qb + 32 * i;
           ok[i] = col >= 0 && col < P.W;
         }
         const int j0 = max(it.h0 - PAD, 0), j1 = min(it.h1 + PAD, P.H);
@@ -550,6 +573,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
             }
             const bool active = u * 8 < min(64, P.Cin - c * 64);
             ptx::mbar_wait(&raw_full[st.i], st.w & 1);
+            if ((aw & 7) == 0 && lane == 0) STRACE(1, st.w * P.SA + st.i);
             if (active) {
               const uint32_t base = sA_u + uint32_t(st.i) * kStage;
               uint4 r[4];
@@ -569,6 +593,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&a_full[st.i]);
+            if ((aw & 7) == 0 && lane == 0) STRACE(2, st.w * P.SA + st.i);
           }
         }
       }
@@ -699,6 +724,25 @@ int stream_pack_create(const float* w, const float* bias, int Cin, int Cout, int
       return fail("stream_pack: weight upload failed");
     }
   }
+  if (ks == 3 && Cout <= 16) {  // row-fold form of the 16-wide 3x3 layers
+    const size_t block = size_t(48) * 128;
+    std::vector<uint8_t> wr(size_t(p->nchunks) * 3 * block, 0);
+    for (int c = 0; c < p->nchunks; ++c)
+      for (int sx = 0; sx < 3; ++sx)
+        for (int pos = 0; pos < 3; ++pos)
+          for (int co = 0; co < Cout; ++co)
+            for (int k = 0; k < 64; ++k) {
+              const int ci = c * 64 + k;
+              if (ci >= Cin) continue;
+              put_bf16(wr.data() + (size_t(c) * 3 + sx) * block, pos * 16 + co, k, w[(size_t((2 - pos) * 3 + sx) * Cin + ci) * CoutP + co]);
+            }
+    p->rfold_bytes = wr.size();
+    if (cudaMalloc(&p->d_wr, wr.size()) != cudaSuccess ||
+        cudaMemcpy(p->d_wr, wr.data(), wr.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      stream_pack_destroy(p);
+      return fail("stream_pack: weight upload failed");
+    }
+  }
   if (ks == 3) {  // wide form: per 64-channel pass nine [NTw x 64ch] blocks per K-chunk, resident in shared memory
     const int NTw = Cout <= 16 ? 16 : 64, npw = (Cout + NTw - 1) / NTw;
     const size_t block = size_t(NTw) * 128, bytes = size_t(p->nchunks) * 9 * block;
@@ -744,6 +788,7 @@ void stream_pack_destroy(StreamPack* p) {
   if (p->d_w) cudaFree(p->d_w);
   if (p->d_wk) cudaFree(p->d_wk);
   if (p->d_ww) cudaFree(p->d_ww);
+  if (p->d_wr) cudaFree(p->d_wr);
   if (p->d_bias) cudaFree(p->d_bias);
   delete p;
 }
@@ -778,13 +823,15 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   const bool wide = fold == 3 && in_mode == kSTma && !fold9;
   P.wide = wide ? 1 : 0;
   P.NT = kfold ? 64 : (wide ? pk.NTw : pk.NT);
-  const bool shift = (fold == 3 && in_mode == kSPro) || fold9;
-  P.NMMA = shift ? 9 * P.NT : (wide ? P.NT : fold * P.NT);
+  static const char* dense_form = getenv("CDAN_DENSE_FORM");  // "rfold" | "shift" (A/B switch), default per layer
+  const bool rfold = fold == 3 && in_mode == kSPro && pk.d_wr && !d.out_nchw && (dense_form && !strcmp(dense_form, "rfold"));  // measured equal or slightly slower than the nine-tap fold on B200
+  const bool shift = (fold == 3 && in_mode == kSPro && !rfold) || fold9;
+  P.NMMA = shift ? 9 * P.NT : (wide ? P.NT : fold * P.NT);  // rfold: 3 * 16
   P.SW = shift ? 3 * P.NT : P.NT;
   P.R = (fold == 3 && !wide) ? std::min(30, 512 / P.SW - 2) : std::min(kMaxR, 512 / P.NT);
   P.nchunks = kfold ? 1 : pk.nchunks;
   P.nS = 1;
-  const int tw_max = shift ? 120 : (wide ? 126 : 128);
+  const int tw_max = shift ? 120 : ((wide || rfold) ? 126 : 128);
   P.strips = ceil_div(d.W, tw_max);
   P.TW = std::min(tw_max, kfold ? (ceil_div(d.W, P.strips) + 3) & ~3 : (ceil_div(d.W, P.strips) + 1) & ~1);
   const int want_segs = std::max(1, ceil_div(sms * 8, d.N * P.strips));
@@ -795,7 +842,7 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   P.in = reinterpret_cast<const bf16*>(d.in); P.in_ld = d.in_ld;
   P.in_nchw = d.in_nchw; P.pre_s = d.pre_scale; P.pre_t = d.pre_shift;
   P.out_ld = d.out_ld; P.out_nchw = d.out_nchw;
-  P.wbytes = uint32_t(kfold ? size_t(192) * 128 : (wide ? pk.wide_bytes : pk.pass_bytes));
+  P.wbytes = uint32_t(kfold ? size_t(192) * 128 : (wide ? pk.wide_bytes : (rfold ? pk.rfold_bytes : pk.pass_bytes)));
   const int tail = 2 * P.nchunks * 64 * 4 + std::max(P.NT, 64) * 4 + 256 + (kfold ? kRawStages * kRawFloats * 4 + 128 : 0);
   P.SA = std::min(kMaxSA, (kSmemLimit - 1024 - int(P.wbytes) - tail) / kStage);
   if (P.SA < 3) return fail("conv_stream: weights leave no room for the activation pipeline");
@@ -831,11 +878,22 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("conv_stream: cuTensorMapEncodeTiled (fp32 input) failed with code " + std::to_string(int(r)));
   }
+#ifdef CDAN_STREAM_TRACE_BUILD
+  static const int trace_launch = getenv("CDAN_STREAM_TRACE") ? atoi(getenv("CDAN_STREAM_TRACE")) : -1;
+  static int launch_ctr = 0;
+  static unsigned long long* d_trace = nullptr;
+  const bool tracing = trace_launch >= 0 && launch_ctr++ == trace_launch;
+  if (tracing) {
+    if (!d_trace) cudaMalloc(&d_trace, 8 * kTraceN * sizeof(unsigned long long));
+    cudaMemsetAsync(d_trace, 0, 8 * kTraceN * sizeof(unsigned long long), stream);
+    P.trace = d_trace;
+  }
+#endif
   const int grid = std::min(P.nitems, sms);
   const int threads = 32 * (kEpiWarp0 + epi_warps(in_mode) + work_warps(in_mode));
   const int npass = kfold ? 1 : (wide ? pk.npass_w : pk.npass);
   for (int pass = 0; pass < npass; ++pass) {
-    P.wpack = kfold ? pk.d_wk : (wide ? pk.d_ww + size_t(pass) * pk.wide_bytes : pk.d_w + size_t(pass) * pk.pass_bytes);
+    P.wpack = kfold ? pk.d_wk : (wide ? pk.d_ww + size_t(pass) * pk.wide_bytes : (rfold ? pk.d_wr : pk.d_w + size_t(pass) * pk.pass_bytes));
     P.bias = pk.d_bias + size_t(pass) * P.NT;
     P.Cout = std::min(P.NT, d.Cout - pass * P.NT);
     P.out = reinterpret_cast<bf16*>(d.out) + size_t(pass) * P.NT;
@@ -849,7 +907,7 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
     if (kfold) rc = d.pool ? launch(conv_stream_kernel<kSNchw, 3, kSPool>) : launch(conv_stream_kernel<kSNchw, 3, kSStore>);
     else if (fold == 3) {
       if (d.out_nchw) rc = in_mode == kSPro ? launch(conv_stream_kernel<kSPro, 3, kSNchwOut>) : launch(conv_stream_kernel<kSTma, 3, kSNchwOut>);
-      else if (in_mode == kSPro) rc = launch(conv_stream_kernel<kSPro, 3, kSStore>);
+      else if (in_mode == kSPro) rc = rfold ? launch(conv_stream_kernel<kSPro, 4, kSStore>) : launch(conv_stream_kernel<kSPro, 3, kSStore>);
       else if (fold9) rc = launch(conv_stream_kernel<kSTma, 9, kSStore>);
       else rc = d.pool ? launch(conv_stream_kernel<kSTma, 3, kSPool>) : launch(conv_stream_kernel<kSTma, 3, kSStore>);
     } else {
@@ -858,6 +916,23 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
     }
     if (rc) return rc;
   }
+#ifdef CDAN_STREAM_TRACE_BUILD
+  if (tracing) {
+    cudaStreamSynchronize(stream);
+    std::vector<unsigned long long> t(8 * kTraceN);
+    cudaMemcpy(t.data(), d_trace, t.size() * 8, cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    for (auto v : t) if (v && v < t0) t0 = v;
+    fprintf(stderr, "STREAM TRACE Cin=%d Cout=%d ks=%d H=%d W=%d N=%d SA=%d R=%d nchunks=%d items=%d SEG=%d strips=%d NMMA=%d\n", d.Cin, d.Cout,
+            d.ks, d.H, d.W, d.N, P.SA, P.R, P.nchunks, P.nitems, P.SEG, P.strips, P.NMMA);
+    const char* names[8] = {"tma_issue", "act_start", "act_done", "mma_start", "mma_issued", "epi_start", "epi_done", "mma_rowgo"};
+    for (int r = 0; r < 8; ++r) {
+      fprintf(stderr, "%-10s", names[r]);
+      for (int i = 0; i < 48; ++i) fprintf(stderr, " %6lld", t[r * kTraceN + i] ? (long long)(t[r * kTraceN + i] - t0) : -1ll);
+      fprintf(stderr, "\n");
+    }
+  }
+#endif
   return 0;
 }
 
