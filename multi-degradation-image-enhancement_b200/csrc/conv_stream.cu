@@ -465,58 +465,59 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
           ptx::mbar_wait(&acc_done[sl0], sr.w & 1);
           ptx::mbar_wait(&acc_done[sl1], sr.w & 1);
           ptx::tc_fence_after_sync();
+          if (q == 0 && lane == 0) STRACE(5, (sr.w * P.R + sr.i) >> 1);
           const bool row_ok = i >= it.h0 && i < it.h1;
           const bool sh0 = !WIDE && sl0 < 2, sh1 = !WIDE && sl1 < 2;
           const uint32_t t0 = lb + uint32_t(sl0 * P.NT), t1 = lb + uint32_t(sl1 * P.NT);
           const uint32_t ts0 = lb + uint32_t((P.R + sl0) * P.NT), ts1 = lb + uint32_t((P.R + sl1) * P.NT);
           bf16* o_row = P.out + ((size_t(it.n) * (P.H >> 1) + (i >> 1)) * (P.W >> 1) + (col >> 1)) * P.out_ld;
           for (int c0 = 0; c0 < P.NT; c0 += 16) {
-            uint32_t pk[4];  // this lane's 8 pooled channels of the 16-channel group, packed bf16
+            // 16 channels of both rows per TMEM round trip (pooling kernels run with <= 512 threads, i.e. 128 registers)
+            uint32_t v0[16], v1[16];
+            if (row_ok) {
+              ptx::tmem_ld16(t0 + c0, v0);
+              ptx::tmem_ld16(t1 + c0, v1);
+              if (sh0 || sh1) {
+                uint32_t w0[16], w1[16];
+                if (sh0) ptx::tmem_ld16(ts0 + c0, w0);
+                if (sh1) ptx::tmem_ld16(ts1 + c0, w1);
+                ptx::tmem_wait_ld();
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const int cc = c0 + 8 * hh;
-              uint32_t v0[8], v1[8];
-              if (row_ok) {
-                ptx::tmem_ld8(t0 + cc, v0);
-                ptx::tmem_ld8(t1 + cc, v1);
-                if (sh0 || sh1) {
-                  uint32_t w0[8], w1[8];
-                  if (sh0) ptx::tmem_ld8(ts0 + cc, w0);
-                  if (sh1) ptx::tmem_ld8(ts1 + cc, w1);
-                  ptx::tmem_wait_ld();
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    if (sh0) v0[e] = __float_as_uint(__uint_as_float(v0[e]) + __uint_as_float(w0[e]));
-                    if (sh1) v1[e] = __float_as_uint(__uint_as_float(v1[e]) + __uint_as_float(w1[e]));
-                  }
-                } else {
-                  ptx::tmem_wait_ld();
+                for (int e = 0; e < 16; ++e) {
+                  if (sh0) v0[e] = __float_as_uint(__uint_as_float(v0[e]) + __uint_as_float(w0[e]));
+                  if (sh1) v1[e] = __float_as_uint(__uint_as_float(v1[e]) + __uint_as_float(w1[e]));
                 }
-              }
-              ptx::tmem_st8_zero(t0 + cc);
-              ptx::tmem_st8_zero(t1 + cc);
-              if (sh0) ptx::tmem_st8_zero(ts0 + cc);
-              if (sh1) ptx::tmem_st8_zero(ts1 + cc);
-              if (row_ok) {
-                const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cc), b1 = *reinterpret_cast<const float4*>(s_bias + cc + 4);
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                float m[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  float x = fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e]));
-                  x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
-                  x += bb[e];  // max commutes with the per-channel bias and with ReLU
-                  m[e] = RELU ? fmaxf(x, 0.f) : x;
-                }
-                // even lane keeps channels [c0, c0+8), odd lane [c0+8, c0+16) of the pooled pixel
-                if ((lane & 1) == hh) {
-                  pk[0] = bf2(m[0], m[1]); pk[1] = bf2(m[2], m[3]); pk[2] = bf2(m[4], m[5]); pk[3] = bf2(m[6], m[7]);
-                }
+              } else {
+                ptx::tmem_wait_ld();
               }
             }
+            ptx::tmem_st16_zero(t0 + c0);
+            ptx::tmem_st16_zero(t1 + c0);
+            if (sh0) ptx::tmem_st16_zero(ts0 + c0);
+            if (sh1) ptx::tmem_st16_zero(ts1 + c0);
             if (row_ok) {
-              const int cg = c0 + ((lane & 1) ? 8 : 0);
-              if (col_ok && cg < P.Cout) *reinterpret_cast<uint4*>(o_row + cg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              // even lane keeps channels [c0, c0+8), odd lane [c0+8, c0+16) of the pooled pixel: exchange the other half
+              // with the horizontal partner and take the max (max commutes with the per-channel bias and with ReLU)
+              const bool odd = lane & 1;
+              float m[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float lo = fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e]));
+                const float hi = fmaxf(__uint_as_float(v0[8 + e]), __uint_as_float(v1[8 + e]));
+                const float mine = odd ? hi : lo, theirs = odd ? lo : hi;
+                const float got = __shfl_xor_sync(0xffffffffu, theirs, 1);  // partner's value of MY channel half
+                m[e] = fmaxf(mine, got);
+              }
+              const int cg = c0 + (odd ? 8 : 0);
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cg), b1 = *reinterpret_cast<const float4*>(s_bias + cg + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                m[e] += bb[e];
+                if (RELU) m[e] = fmaxf(m[e], 0.f);
+              }
+              if (col_ok && cg < P.Cout)
+                *reinterpret_cast<uint4*>(o_row + cg) = make_uint4(bf2(m[0], m[1]), bf2(m[2], m[3]), bf2(m[4], m[5]), bf2(m[6], m[7]));
             }
           }
           ptx::tmem_wait_st();
@@ -526,6 +527,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
             ptx::mbar_arrive(&acc_free[sl0]);
             ptx::mbar_arrive(&acc_free[sl1]);
           }
+          if (q == 0 && lane == 0) STRACE(6, (sr.w * P.R + sr.i) >> 1);
           sr.add(2 * kEG, P.R);
           i += 2 * kEG;
         }
@@ -608,6 +610,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
         const int j0 = max(it.h0 - 1, 0), j1 = min(it.h1 + 1, P.H);
         for (int j = j0; j < j1; ++j) {
           ptx::mbar_wait(&raw_full[rr.i], rr.w & 1);
+          if (aw == 0 && lane == 0) STRACE(1, st.w * P.SA + st.i);
           const float* raw = s_raw + rr.i * kRawFloats + p + 3;
           float x[9];
 #pragma unroll
@@ -624,6 +627,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&a_full[st.i]);
+          if (aw == 0 && lane == 0) STRACE(2, st.w * P.SA + st.i);
           st.step(P.SA);
           rr.step(kRawStages);
         }

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
           if (IN_MODE != kInNchw3) {
             // TMA mode: the tile feeds the MMA directly; producer mode: it lands "raw" and warps 8-15 activate it
             uint64_t* full = IN_MODE == kInTma ? &a_full[sa] : &raw_full[sa];
-            ptx::mbar_wait_relaxed(&a_empty[sa], pa ^ 1);
+            ptx::mbar_wait(&a_empty[sa], pa ^ 1);
             ptx::mbar_arrive_expect_tx(full, uint32_t(P.a_rows) * 128u);
             ptx::tma_load_4d(sA + size_t(sa) * P.a_stage_bytes, &tmapA, c * 64, w0 - P.halo, h0 - P.halo, n, full);
             if (++sa == P.SA) { sa = 0; pa ^= 1; }
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
           for (int j = 0; j < P.bst_per_chunk; ++j) {
             const int ntap = min(P.tps, P.taps - j * P.tps);
             const uint32_t bytes = uint32_t(ntap) * P.NT * 128u;
-            ptx::mbar_wait_relaxed(&b_empty[sb], pb ^ 1);
+            ptx::mbar_wait(&b_empty[sb], pb ^ 1);
             ptx::mbar_arrive_expect_tx(&b_full[sb], bytes);
             ptx::bulk_g2s(sB + size_t(sb) * P.b_stage_bytes, wsrc + size_t(j) * P.tps * P.NT * 128, bytes, &b_full[sb]);
             if (++sb == P.SB) { sb = 0; pb ^= 1; }
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
         asm volatile("bar.sync 1, 128;" ::: "memory");
         cur_pass = pass;
       }
-      ptx::mbar_wait_relaxed(&acc_full[as], pacc, 32);
+      ptx::mbar_wait(&acc_full[as], pacc);
       ptx::tc_fence_after_sync();
       const uint32_t acc_col = tmem_base + uint32_t(as * P.NMB * P.NT) + (uint32_t(q * 32) << 16);
       const int cbase = pass * P.NT;  // first output channel of this pass
@@ -270,11 +270,13 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
             xpar ^= 1;
           } else if (P.out_nchw) {
             if (valid) {
-              for (int j = 0; j < 16 && cg + j < P.Cout; ++j) {
-                float f = v[j];
-                if (P.sigmoid) f = 1.0f / (1.0f + __expf(-f));
-                P.out_nchw[((size_t(n) * P.Cout + cg + j) * P.H + h) * P.W + w] = f;
-              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cg + j < P.Cout) {
+                  float f = v[j];
+                  if (P.sigmoid) f = 1.0f / (1.0f + __expf(-f));
+                  P.out_nchw[((size_t(n) * P.Cout + cg + j) * P.H + h) * P.W + w] = f;
+                }
             }
           } else if (valid && cg < P.Cout) {
             bf16* o = P.out + ((size_t(n) * P.H + h) * P.W + w) * P.out_ld + cg;
@@ -287,7 +289,9 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
               *reinterpret_cast<uint4*>(o) = u0;
               *reinterpret_cast<uint4*>(o + 8) = u1;
             } else {
-              for (int j = 0; j < 16 && cg + j < P.Cout; ++j) o[j] = __float2bfloat16_rn(v[j]);
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cg + j < P.Cout) o[j] = __float2bfloat16_rn(v[j]);
             }
           }
         }
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
           if (IN_MODE == kInNchw3) {
             // fp32 planar 3-channel network input -> one 16-channel group (3 real + 13 zero) per pixel.
             // Loads of a whole batch of pixels are issued before any is consumed (memory-level parallelism).
-            ptx::mbar_wait_relaxed(&a_empty[sa], pa ^ 1);
+            ptx::mbar_wait(&a_empty[sa], pa ^ 1);
             const size_t plane = size_t(P.H) * P.W;
             const float* img = P.in_nchw + size_t(n) * 3 * plane;
             constexpr int U = 4;
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
             const int step_r = step / P.WP, step_w = step - step_r * P.WP;
             int q = pw * ppi + psub;
             int rr = q / P.WP, wi = q - rr * P.WP;
-            ptx::mbar_wait_relaxed(&raw_full[sa], pa);
+            ptx::mbar_wait(&raw_full[sa], pa);
             if (ch0 < P.Cin) {
               for (; q < P.a_rows; q += step) {
                 const int h = h0 - P.halo + rr, w = w0 - P.halo + wi;
