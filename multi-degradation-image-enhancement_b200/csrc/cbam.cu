@@ -150,31 +150,39 @@ __global__ void __launch_bounds__(256) compress_kernel(const T* __restrict__ x, 
 }
 
 // SpatialGate (models/cbam.py:72-82): 7x7 conv over the 2-channel map, zero pad 3, no bias, BN(1), sigmoid.
+// One 16x64 tile per block: the tile + 3-pixel halo of comp is staged in shared memory once (zeros outside the image),
+// then every thread evaluates four pixels from shared memory (98 FMAs each).
+constexpr int kSgTH = 16, kSgTW = 64, kSgHH = kSgTH + 6, kSgHW = kSgTW + 6;
 __global__ void __launch_bounds__(256) spatial_gate_kernel(const float* __restrict__ comp, const float* __restrict__ w7,
-                                                            float bn_a, float bn_b, float* __restrict__ sgate, int N,
-                                                            int H, int W) {
+                                                            float bn_a, float bn_b, float* __restrict__ sgate, int H,
+                                                            int W) {
+  __shared__ float2 s_c[kSgHH * kSgHW];
   __shared__ float w[98];
+  const int n = blockIdx.z, y0 = blockIdx.y * kSgTH, x0 = blockIdx.x * kSgTW;
   if (threadIdx.x < 98) w[threadIdx.x] = w7[threadIdx.x];
+  const float2* cn = reinterpret_cast<const float2*>(comp) + size_t(n) * H * W;
+  for (int q = threadIdx.x; q < kSgHH * kSgHW; q += 256) {
+    const int hh = q / kSgHW, ww = q - hh * kSgHW;
+    const int y = y0 - 3 + hh, x = x0 - 3 + ww;
+    s_c[q] = (y >= 0 && y < H && x >= 0 && x < W) ? cn[size_t(y) * W + x] : make_float2(0.f, 0.f);
+  }
   __syncthreads();
-  const size_t total = size_t(N) * H * W;
-  for (size_t pix = blockIdx.x * size_t(blockDim.x) + threadIdx.x; pix < total; pix += size_t(gridDim.x) * blockDim.x) {
-    const int x = int(pix % W), y = int((pix / W) % H);
-    const size_t nb = pix - (size_t(y) * W + x);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int q = threadIdx.x + 256 * k;
+    const int hh = q / kSgTW, ww = q - hh * kSgTW;
+    const int y = y0 + hh, x = x0 + ww;
+    if (y >= H || x >= W) continue;
     float acc = 0.f;
 #pragma unroll
-    for (int r = 0; r < 7; ++r) {
-      const int yy = y + r - 3;
-      if (yy < 0 || yy >= H) continue;
+    for (int r = 0; r < 7; ++r)
 #pragma unroll
-      for (int s = 0; s < 7; ++s) {
-        const int xx = x + s - 3;
-        if (xx < 0 || xx >= W) continue;
-        const float2 c = *reinterpret_cast<const float2*>(comp + (nb + size_t(yy) * W + xx) * 2);
-        acc = fmaf(w[r * 7 + s], c.x, acc);
-        acc = fmaf(w[49 + r * 7 + s], c.y, acc);
+      for (int c = 0; c < 7; ++c) {
+        const float2 cp = s_c[(hh + r) * kSgHW + ww + c];
+        acc = fmaf(w[r * 7 + c], cp.x, acc);
+        acc = fmaf(w[49 + r * 7 + c], cp.y, acc);
       }
-    }
-    sgate[pix] = 1.0f / (1.0f + expf(-(bn_a * acc + bn_b)));
+    sgate[(size_t(n) * H + y) * W + x] = 1.0f / (1.0f + expf(-(bn_a * acc + bn_b)));
   }
 }
 
@@ -230,7 +238,7 @@ int cbam_typed(const void* x, int x_ld, const void* mul, int mul_ld, void* out, 
   const int lpp = vecs < 32 ? vecs : 32;
   compress_kernel<T><<<grid_for(npix * lpp), 256, 0, s>>>((const T*)x, x_ld, C, HW, npix, sc.gate, sc.comp);
   CDAN_CUDA_OK(cudaGetLastError());
-  spatial_gate_kernel<<<grid_for(npix), 256, 0, s>>>(sc.comp, wt.w7, wt.bn_a, wt.bn_b, sc.sgate, N, H, W);
+  spatial_gate_kernel<<<dim3(ceil_div(W, kSgTW), ceil_div(H, kSgTH), N), 256, 0, s>>>(sc.comp, wt.w7, wt.bn_a, wt.bn_b, sc.sgate, H, W);
   CDAN_CUDA_OK(cudaGetLastError());
   apply_kernel<T><<<grid_for(npix * vecs), 256, 0, s>>>((const T*)x, x_ld, sc.gate, sc.sgate, (const T*)mul, mul_ld,
                                                         (T*)out, out_ld, C, HW, npix);

@@ -811,6 +811,13 @@ bool conv_stream_supported(const ConvDesc& d, const StreamPack& pk) {
   return d.out_ld % 8 == 0;
 }
 
+// Number of kernels conv_stream_launch issues for this convolution (output-channel passes).
+int conv_stream_kernel_count(const ConvDesc& d, const StreamPack& pk) {
+  if (d.in_nchw) return 1;
+  if (d.ks == 3 && !d.pre_scale) return (pk.d_w && pk.NT == 16 && !d.pool) ? 1 : pk.npass_w;
+  return d.ks == 3 ? 1 : pk.npass;
+}
+
 int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t stream) {
   if (!conv_stream_supported(d, pk)) return fail("conv_stream: unsupported convolution shape");
   const bool kfold = d.in_nchw != nullptr;

@@ -554,6 +554,12 @@ bool conv_umma_supported(const ConvDesc& d) {
   return true;
 }
 
+int conv_umma_kernel_count(const ConvDesc& d, const UmmaPack& pk) {
+  static const bool use_stream = !(getenv("CDAN_CONV_STREAM") && atoi(getenv("CDAN_CONV_STREAM")) == 0);
+  if (use_stream && pk.stream && conv_stream_supported(d, *pk.stream)) return conv_stream_kernel_count(d, *pk.stream);
+  return 1;
+}
+
 int conv_umma_launch(const ConvDesc& d, const UmmaPack& pk, cudaStream_t stream) {
   if (!conv_umma_supported(d)) return fail("conv_umma: unsupported convolution shape");
   if (pk.Cin != d.Cin || pk.Cout != d.Cout || pk.ks != d.ks) return fail("conv_umma: weight pack does not match");

@@ -20,6 +20,9 @@ int stream_pack_create(const float* w_taps_cin_coutp, const float* bias_coutp, i
 void stream_pack_destroy(StreamPack* p);
 bool conv_stream_supported(const ConvDesc& d, const StreamPack& pack);
 int conv_stream_launch(const ConvDesc& d, const StreamPack& pack, cudaStream_t stream);
+int conv_stream_kernel_count(const ConvDesc& d, const StreamPack& pack);
+// Kernels conv_umma_launch issues for this convolution (1, or one per output-channel pass of the streaming kernel).
+int conv_umma_kernel_count(const ConvDesc& d, const UmmaPack& pack);
 int conv_umma_launch(const ConvDesc& d, const UmmaPack& pack, cudaStream_t stream);
 
 }  // namespace cdan

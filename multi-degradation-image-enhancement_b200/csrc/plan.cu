@@ -309,7 +309,7 @@ int run_conv(cdan_plan* p, ConvId id, int N, int H, int W, const void* in, int i
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return fail("kernel of layer '" + L.name + "' failed: " + cudaGetErrorString(e));
   }
-  p->launches += 1;
+  p->launches += umma ? conv_umma_kernel_count(d, *L.umma) : 1;
   return 0;
 }
 

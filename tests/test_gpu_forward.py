@@ -142,3 +142,21 @@ def test_host_buffer_entry_point(cuda_device):
         y_dev = net(x.to(cuda_device)).cpu()
     assert torch.equal(y_host, y_dev)
     assert net.native_plan().last_launch_count > 0
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_host_buffer_pipeline_chunks(cuda_device, dtype):
+    """cdan_forward_host splits the batch into sub-batches (H2D / forward / D2H on three streams, double-buffered
+    staging): ragged tails, more chunks than staging slots and repeated calls must all equal the device-resident forward."""
+    sd = stress_state_dict(1234)
+    net = make_net(sd, dtype, cuda_device)
+    plan = net.native_plan()
+    x = ramp_input(7, 24, 40, seed=11)
+    with torch.no_grad():
+        y_dev = net(x.to(cuda_device)).cpu()
+    for chunk in (1, 2, 3, 8):
+        plan.set_option("host_chunk", chunk)
+        for _ in range(2):
+            y_host = plan.forward_host(x.pin_memory())
+            assert torch.equal(y_host, y_dev), chunk
+    plan.set_option("host_chunk", 8)
