@@ -48,7 +48,10 @@ struct StreamPack {
 
 namespace {
 
-enum SIn : int { kSTma = 0, kSPro = 1, kSNchw = 2 };
+// kSPro2 = kSPro in a half-size CTA (512 threads, 256 TMEM columns, <= 113 KB shared memory) so that TWO CTAs share an
+// SM: every role of this kernel is a single-warp latency chain, and two independent pipelines per SM overlap them.
+enum SIn : int { kSTma = 0, kSPro = 1, kSNchw = 2, kSPro2 = 3 };
+__host__ __device__ constexpr bool is_pro(int in_mode) { return in_mode == 1 || in_mode == 3; }
 enum SEpi : int { kSStore = 0, kSPool = 1, kSNchwOut = 2 };
 
 constexpr int kStage = 16384;  // one input row: 128 pixels x 64 channels bf16
@@ -61,8 +64,8 @@ constexpr int kMaxR = 32;
 // workers (16 warps = two groups alternating stages for the dense pre-activation, 4 for conv1's row builder, none for
 // TMA-fed layers).
 constexpr int kEpiWarp0 = 4;
-__host__ __device__ constexpr int epi_warps(int) { return 8; }
-__host__ __device__ constexpr int work_warps(int in_mode) { return in_mode == 0 ? 0 : (in_mode == 1 ? 16 : 4); }
+__host__ __device__ constexpr int epi_warps(int in_mode) { return in_mode == 3 ? 4 : 8; }
+__host__ __device__ constexpr int work_warps(int in_mode) { return in_mode == 0 ? 0 : (in_mode == 1 ? 16 : (in_mode == 3 ? 8 : 4)); }
 
 struct SParams {
   int N, H, W, Cin;
@@ -126,7 +129,7 @@ struct Ring {
 };
 
 template <int IN, int FOLD, int EPI>
-__global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(IN)), 1) conv_stream_kernel(const __grid_constant__ CUtensorMap tmapA, const SParams P) {
+__global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(IN)), IN == 3 ? 2 : 1) conv_stream_kernel(const __grid_constant__ CUtensorMap tmapA, const SParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -149,13 +152,15 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
   constexpr int kEG = kEpiWarps / 4;  // epilogue groups
   // SHIFT: all nine taps folded into N (N = 9*NT); lane l of warp-quarter q holds strip pixel 30*q + l - 1, the
   // epilogue adds the three horizontal-tap column groups of lanes l-1, l, l+1 (valid outputs: l = 1..30).
-  constexpr bool SHIFT = (FOLD == 3 && IN == kSPro) || FOLD == 9;
+  constexpr bool SHIFT = (FOLD == 3 && is_pro(IN)) || FOLD == 9;
+  constexpr int kGroups = kWorkWarps / 8;  // worker groups (kSPro: 2, kSPro2: 1)
+  constexpr uint32_t kTmemCols = IN == kSPro2 ? 256 : 512;
   constexpr bool WIDE = FOLD == 3 && IN == kSTma;
-  constexpr bool RELU = IN != kSPro;  // dense-block layers have no output ReLU; ConvBlock / decoder convs always do
+  constexpr bool RELU = !is_pro(IN);  // dense-block layers have no output ReLU; ConvBlock / decoder convs always do
 
   if (tid == 0) {
     for (int i = 0; i < kMaxSA; ++i) {
-      ptx::mbar_init(&a_full[i], IN == kSTma ? 1 : (IN == kSPro ? 8 : 4));
+      ptx::mbar_init(&a_full[i], IN == kSTma ? 1 : (is_pro(IN) ? 8 : 4));
       ptx::mbar_init(&a_empty[i], 1);
       ptx::mbar_init(&raw_full[i], 1);
       if (i < kRawStages) ptx::mbar_init(&raw_empty[i], 4);
@@ -174,11 +179,11 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
 #endif
   }
   if (warp == 2) {
-    ptx::tmem_alloc(&tmem_base_s, 512);
+    ptx::tmem_alloc(&tmem_base_s, kTmemCols);
     ptx::tmem_relinquish();
   }
   for (int i = tid; i < P.nchunks * 64; i += blockDim.x) {
-    const bool ok = IN == kSPro && i < P.Cin;
+    const bool ok = is_pro(IN) && i < P.Cin;
     s_pre_s[i] = ok ? P.pre_s[i] : 0.f;
     s_pre_t[i] = ok ? P.pre_t[i] : 0.f;
   }
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
   const uint32_t tmem_base = tmem_base_s;
   if (PAD && warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {  // ring accumulators start at zero
     const uint32_t lb = tmem_base + (uint32_t((warp & 3) * 32) << 16);
-    for (int c = 0; c < 512; c += 16) ptx::tmem_st16_zero(lb + c);
+    for (int c = 0; c < int(kTmemCols); c += 16) ptx::tmem_st16_zero(lb + c);
     ptx::tmem_wait_st();
   }
   ptx::tc_fence_before_sync();
@@ -538,7 +543,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
   } else if (warp >= kWorkWarp0) {
     // ============================================================ A-stage workers
     const int aw = warp - kWorkWarp0;
-    if (IN == kSPro) {
+    if (is_pro(IN)) {
       // The raw NHWC bf16 row was delivered by TMA (zero outside the image / beyond Cin).  Apply the dense-block
       // pre-activation relu(s*x+t) in place in fp32; pixels outside the image stay zero, i.e. the conv padding is applied
       // AFTER the activation (reference models/cdan.py:41-46).  Thread -> (16-byte channel group u, pixels qb + 32*i).
@@ -550,7 +555,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
       uint32_t off[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) off[i] = ptx::sw128_offset(uint32_t(qb + 32 * i), uint32_t(u));
-      float4 s0, s1, t0, t1;
+      __nv_bfloat162 sc[4], sh[4];
       int cached_c = -1;
       Ring st;
       int turn = 0;  // stage parity: this group works when turn == grp
@@ -565,12 +570,18 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
         const int j0 = max(it.h0 - PAD, 0), j1 = min(it.h1 + PAD, P.H);
         for (int j = j0; j < j1; ++j) {
           for (int c = 0; c < P.nchunks; ++c, turn ^= 1, st.step(P.SA)) {
-            if (turn != grp) continue;
+            if (kGroups == 2 && turn != grp) continue;
             if (c != cached_c) {
-              s0 = *reinterpret_cast<const float4*>(s_pre_s + c * 64 + u * 8);
-              s1 = *reinterpret_cast<const float4*>(s_pre_s + c * 64 + u * 8 + 4);
-              t0 = *reinterpret_cast<const float4*>(s_pre_t + c * 64 + u * 8);
-              t1 = *reinterpret_cast<const float4*>(s_pre_t + c * 64 + u * 8 + 4);
+              // BN scale / shift of this thread's 8 channels as packed bf16x2 (rounded once here): the activation is
+              // one HFMA2.BF16 with ReLU per channel pair instead of unpack + 2 FFMA + pack
+              const float4 fs0 = *reinterpret_cast<const float4*>(s_pre_s + c * 64 + u * 8);
+              const float4 fs1 = *reinterpret_cast<const float4*>(s_pre_s + c * 64 + u * 8 + 4);
+              const float4 ft0 = *reinterpret_cast<const float4*>(s_pre_t + c * 64 + u * 8);
+              const float4 ft1 = *reinterpret_cast<const float4*>(s_pre_t + c * 64 + u * 8 + 4);
+              sc[0] = __floats2bfloat162_rn(fs0.x, fs0.y); sc[1] = __floats2bfloat162_rn(fs0.z, fs0.w);
+              sc[2] = __floats2bfloat162_rn(fs1.x, fs1.y); sc[3] = __floats2bfloat162_rn(fs1.z, fs1.w);
+              sh[0] = __floats2bfloat162_rn(ft0.x, ft0.y); sh[1] = __floats2bfloat162_rn(ft0.z, ft0.w);
+              sh[2] = __floats2bfloat162_rn(ft1.x, ft1.y); sh[3] = __floats2bfloat162_rn(ft1.z, ft1.w);
               cached_c = c;
             }
             const bool active = u * 8 < min(64, P.Cin - c * 64);
@@ -583,10 +594,9 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
               for (int i = 0; i < 4; ++i) r[i] = ptx::lds128(base + off[i]);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                r[i].x = ptx::cvt_relu_bf16x2(fmaf(bflo(r[i].x), s0.x, t0.x), fmaf(bfhi(r[i].x), s0.y, t0.y));
-                r[i].y = ptx::cvt_relu_bf16x2(fmaf(bflo(r[i].y), s0.z, t0.z), fmaf(bfhi(r[i].y), s0.w, t0.w));
-                r[i].z = ptx::cvt_relu_bf16x2(fmaf(bflo(r[i].z), s1.x, t1.x), fmaf(bfhi(r[i].z), s1.y, t1.y));
-                r[i].w = ptx::cvt_relu_bf16x2(fmaf(bflo(r[i].w), s1.z, t1.z), fmaf(bfhi(r[i].w), s1.w, t1.w));
+                __nv_bfloat162* v = reinterpret_cast<__nv_bfloat162*>(&r[i]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = __hfma2_relu(v[e], sc[e], sh[e]);
               }
 #pragma unroll
               for (int i = 0; i < 4; ++i)
@@ -639,7 +649,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc(tmem_base, 512);
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -834,12 +844,25 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   const bool wide = fold == 3 && in_mode == kSTma && !fold9;
   P.wide = wide ? 1 : 0;
   P.NT = kfold ? 64 : (wide ? pk.NTw : pk.NT);
+  // Optional (CDAN_DUAL=1): dense pre-activation layers as two half-size CTAs per SM (kSPro2) when their weights leave
+  // room for >= 3 stages in 110 KB; 3x3 layers then use the row-fold form (16 TMEM columns per ring slot fit a 256-column
+  // allocation).  Measured 3 % slower than one full-size CTA per SM on B200, so it is off by default.
+  static const bool dual_enabled = getenv("CDAN_DUAL") && atoi(getenv("CDAN_DUAL")) != 0;
+  constexpr int kSmemLimit2 = 110 * 1024;  // 2 x (dynamic + 1 KB align slack + static barriers + 1 KB reserved) <= 228 KB
+  bool dual = false;
+  if (dual_enabled && in_mode == kSPro && !d.pool) {
+    const size_t wb = fold == 3 ? (pk.d_wr && !d.out_nchw ? pk.rfold_bytes : 0) : (pk.NT <= 64 ? pk.pass_bytes : 0);
+    const int tail2 = 2 * pk.nchunks * 64 * 4 + 64 * 4 + 256;
+    dual = wb > 0 && (kSmemLimit2 - 1024 - int(wb) - tail2) / kStage >= 3;
+  }
   static const char* dense_form = getenv("CDAN_DENSE_FORM");  // "rfold" | "shift" (A/B switch), default per layer
-  const bool rfold = fold == 3 && in_mode == kSPro && pk.d_wr && !d.out_nchw && (dense_form && !strcmp(dense_form, "rfold"));  // measured equal or slightly slower than the nine-tap fold on B200
+  const bool rfold = fold == 3 && in_mode == kSPro && pk.d_wr && !d.out_nchw && (dual || (dense_form && !strcmp(dense_form, "rfold")));  // measured equal or slightly slower than the nine-tap fold on B200
   const bool shift = (fold == 3 && in_mode == kSPro && !rfold) || fold9;
   P.NMMA = shift ? 9 * P.NT : (wide ? P.NT : fold * P.NT);  // rfold: 3 * 16
   P.SW = shift ? 3 * P.NT : P.NT;
-  P.R = (fold == 3 && !wide) ? std::min(30, 512 / P.SW - 2) : std::min(kMaxR, 512 / P.NT);
+  const int tmem_cols = dual ? 256 : 512;
+  P.R = (fold == 3 && !wide) ? std::min(30, tmem_cols / P.SW - 2) : std::min(kMaxR, tmem_cols / P.NT);
+  P.R &= ~1;
   P.nchunks = kfold ? 1 : pk.nchunks;
   P.nS = 1;
   const int tw_max = shift ? 120 : ((wide || rfold) ? 126 : 128);
@@ -855,7 +878,7 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   P.out_ld = d.out_ld; P.out_nchw = d.out_nchw;
   P.wbytes = uint32_t(kfold ? size_t(192) * 128 : (wide ? pk.wide_bytes : (rfold ? pk.rfold_bytes : pk.pass_bytes)));
   const int tail = 2 * P.nchunks * 64 * 4 + std::max(P.NT, 64) * 4 + 256 + (kfold ? kRawStages * kRawFloats * 4 + 128 : 0);
-  P.SA = std::min(kMaxSA, (kSmemLimit - 1024 - int(P.wbytes) - tail) / kStage);
+  P.SA = std::min(kMaxSA, ((dual ? kSmemLimit2 : kSmemLimit) - 1024 - int(P.wbytes) - tail) / kStage);
   if (P.SA < 3) return fail("conv_stream: weights leave no room for the activation pipeline");
   const int smem_bytes = P.SA * kStage + 1024 + int(P.wbytes) + tail + 1024;
 
@@ -900,8 +923,8 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
     P.trace = d_trace;
   }
 #endif
-  const int grid = std::min(P.nitems, sms);
-  const int threads = 32 * (kEpiWarp0 + epi_warps(in_mode) + work_warps(in_mode));
+  const int grid = std::min(P.nitems, dual ? 2 * sms : sms);
+  const int threads = 32 * (kEpiWarp0 + epi_warps(dual ? kSPro2 : in_mode) + work_warps(dual ? kSPro2 : in_mode));
   const int npass = kfold ? 1 : (wide ? pk.npass_w : pk.npass);
   for (int pass = 0; pass < npass; ++pass) {
     P.wpack = kfold ? pk.d_wk : (wide ? pk.d_ww + size_t(pass) * pk.wide_bytes : (rfold ? pk.d_wr : pk.d_w + size_t(pass) * pk.pass_bytes));
@@ -918,11 +941,13 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
     if (kfold) rc = d.pool ? launch(conv_stream_kernel<kSNchw, 3, kSPool>) : launch(conv_stream_kernel<kSNchw, 3, kSStore>);
     else if (fold == 3) {
       if (d.out_nchw) rc = in_mode == kSPro ? launch(conv_stream_kernel<kSPro, 3, kSNchwOut>) : launch(conv_stream_kernel<kSTma, 3, kSNchwOut>);
+      else if (in_mode == kSPro && dual) rc = launch(conv_stream_kernel<kSPro2, 4, kSStore>);
       else if (in_mode == kSPro) rc = rfold ? launch(conv_stream_kernel<kSPro, 4, kSStore>) : launch(conv_stream_kernel<kSPro, 3, kSStore>);
       else if (fold9) rc = launch(conv_stream_kernel<kSTma, 9, kSStore>);
       else rc = d.pool ? launch(conv_stream_kernel<kSTma, 3, kSPool>) : launch(conv_stream_kernel<kSTma, 3, kSStore>);
     } else {
-      if (d.out_nchw) rc = in_mode == kSPro ? launch(conv_stream_kernel<kSPro, 1, kSNchwOut>) : launch(conv_stream_kernel<kSTma, 1, kSNchwOut>);
+      if (dual) rc = d.out_nchw ? launch(conv_stream_kernel<kSPro2, 1, kSNchwOut>) : launch(conv_stream_kernel<kSPro2, 1, kSStore>);
+      else if (d.out_nchw) rc = in_mode == kSPro ? launch(conv_stream_kernel<kSPro, 1, kSNchwOut>) : launch(conv_stream_kernel<kSTma, 1, kSNchwOut>);
       else rc = in_mode == kSPro ? launch(conv_stream_kernel<kSPro, 1, kSStore>) : launch(conv_stream_kernel<kSTma, 1, kSStore>);
     }
     if (rc) return rc;

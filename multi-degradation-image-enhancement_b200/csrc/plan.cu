@@ -208,6 +208,14 @@ void free_weights(cdan_plan* p) {
   p->loaded = false;
 }
 
+// Channel stride of the final dense block's concat buffer: 80 channels are used, the pixel is padded to 128 channels
+// (256 B) so that every channel-prefix read starts and ends on a 64-byte DRAM atom (measured: 160-byte pixels make the
+// 128-byte prefix of layer 3 fetch the whole buffer and cost ~6 % of the step; 192-byte pixels are worse still).
+int fd_ld() {
+  static const int v = getenv("CDAN_FD_LD") ? atoi(getenv("CDAN_FD_LD")) : 128;
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------ workspace
 size_t carve(Buffers& b, char* base, DType dt, int N, int H, int W) {
   const size_t es = dt == kF32 ? 4 : 2;
@@ -236,7 +244,7 @@ size_t carve(Buffers& b, char* base, DType dt, int N, int H, int W) {
   b.U3 = take(p2 * 64 * es);
   b.C3 = take(p2 * 64 * es);
   b.T4 = take(p2 * 8 * es);
-  b.FD = take(p1 * 80 * es);  // final dense block concat: 3 input channels padded to 16 (32-byte sectors), then 4 x 16
+  b.FD = take(p1 * size_t(fd_ld()) * es);  // final dense block concat: 3 input channels padded to 16, then 4 x 16
   size_t sc = 0;
   sc = std::max(sc, cbam_scratch_floats(N, 512, H / 8, W / 8));
   sc = std::max(sc, cbam_scratch_floats(N, 256, H / 8, W / 8));
@@ -389,10 +397,10 @@ int forward_impl(cdan_plan* p, cudaStream_t s, const float* x, float* y, int N, 
   CDAN_TRY(run_up_add(p, 3, b.T3, 64, b.D1, 128, b.U3, N, H2, W2, 1, s));
   CDAN_TRY(run_cbam(p, 3, b.U3, b.DN1, b.C3, N, H2, W2, true, s));
   CDAN_TRY(run_conv(p, DEC4, N, H2, W2, b.C3, 64, b.T4, 8, 0, s));
-  { SpanGuard span(p, s, "glue|up_add_input"); CDAN_TRY(up_add_input_launch(dt, b.T4, 8, x, b.FD, 80, 16, N, H, W, s)); }
+  { SpanGuard span(p, s, "glue|up_add_input"); CDAN_TRY(up_add_input_launch(dt, b.T4, 8, x, b.FD, fd_ld(), 16, N, H, W, s)); }
   p->launches += 1;
   // final DenseBlock(3,3,16,4) + sigmoid, written straight to the caller's fp32 NCHW output
-  CDAN_TRY(run_dense(p, FDL0, N, H, W, b.FD, 80, 16, nullptr, 3, s, y));
+  CDAN_TRY(run_dense(p, FDL0, N, H, W, b.FD, fd_ld(), 16, nullptr, 3, s, y));
 
   auto& st = p->stages;
   st.clear();
@@ -411,7 +419,7 @@ int forward_impl(cdan_plan* p, cudaStream_t s, const float* x, float* y, int N, 
   st["dec.bn3"] = {b.T3, 64, 64, H4, W4};
   st["dec.gated3"] = {b.C3, 64, 64, H2, W2};
   st["dec.bn4"] = {b.T4, 3, 8, H2, W2};
-  st["dec.final_in"] = {b.FD, 3, 80, H, W};
+  st["dec.final_in"] = {b.FD, 3, fd_ld(), H, W};
   return 0;
 }
 

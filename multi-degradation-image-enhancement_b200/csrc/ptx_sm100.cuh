@@ -82,11 +82,30 @@ static __device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity)
   __trap();
 #endif
 }
+// The poll loop lives in PTX (try_wait with a suspend-time hint, 4 instructions per wake-up): a waiting warp wakes up
+// about ten times per wait on B200, and the compiler-generated C++ loop cost ~16 issue slots per wake-up — a third of
+// all instructions the streaming convolution executed.  Still bounded: after CDAN_MBAR_MAX_POLLS failed polls it traps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t polls = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++polls > CDAN_MBAR_MAX_POLLS) mbar_timeout(bar, parity);
-  }
+  uint32_t timed_out;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .u32 cnt;\n\t"
+      "mov.u32 cnt, 0;\n\t"
+      "mov.u32 %0, 0;\n"
+      "CDAN_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "@p bra CDAN_WAIT_DONE;\n\t"
+      "add.u32 cnt, cnt, 1;\n\t"
+      "setp.lt.u32 p, cnt, %4;\n\t"
+      "@p bra CDAN_WAIT_LOOP;\n\t"
+      "mov.u32 %0, 1;\n"
+      "CDAN_WAIT_DONE:\n\t"
+      "}"
+      : "=r"(timed_out)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(CDAN_MBAR_SUSPEND_NS), "r"(CDAN_MBAR_MAX_POLLS)
+      : "memory");
+  if (timed_out) mbar_timeout(bar, parity);
 }
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns = 64) {
   uint32_t polls = 0;
