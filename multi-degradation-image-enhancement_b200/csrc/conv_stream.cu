@@ -88,6 +88,7 @@ struct SParams {
   bf16* out;
   int out_ld;
   float* out_nchw;
+  int ablate;  // debug (CDAN_ABLATE bitmask): 1 skip epilogue global stores, 2 skip worker math, 4 skip MMA issue, 8 skip epilogue TMEM traffic
   unsigned long long* trace;  // timeline of CTA 0 (debug builds with -DCDAN_STREAM_TRACE_BUILD): [role][kTraceN]
 };
 constexpr int kTraceN = 256;
@@ -288,7 +289,8 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
               // One elected lane issues (ptxas keeps descriptors in uniform registers inside an elect.sync region;
               // a per-thread predicate on the instruction instead costs a vote + R2UR.BROADCAST sequence per MMA).
               if (ptx::elect_one()) {
-                if (WIDE) {
+                if (P.ablate & 4) {
+                } else if (WIDE) {
                   // nine taps: kernel row r feeds accumulator row G + (2 - r) (its own ring slot), the horizontal tap
                   // s is the A view shifted by s pixels; weight blocks are ordered [r*3+s]
 #pragma unroll
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
           ptx::mbar_wait(&acc_done[slot], sr.w & 1);
           ptx::tc_fence_after_sync();
           if (q == 0 && lane == 0) STRACE(5, sr.w * P.R + sr.i);
-          const bool row_ok = i >= it.h0 && i < it.h1;
+          const bool row_ok = i >= it.h0 && i < it.h1 && !(P.ablate & 8);
           const bool shadow = PAD && !WIDE && slot < 2;
           const uint32_t tm = lb + uint32_t(slot * P.SW), ts = lb + uint32_t((P.R + slot) * P.SW);
           // 8 output channels at a time keeps the live register set small (spills are L2 round trips here: with
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
               }
-              if (col_ok) {
+              if (col_ok && !(P.ablate & 1)) {
                 if (EPI == kSNchwOut) {
                   const size_t plane = size_t(P.H) * P.W;
 #pragma unroll
@@ -587,7 +589,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
             const bool active = u * 8 < min(64, P.Cin - c * 64);
             ptx::mbar_wait(&raw_full[st.i], st.w & 1);
             if ((aw & 7) == 0 && lane == 0) STRACE(1, st.w * P.SA + st.i);
-            if (active) {
+            if (active && !(P.ablate & 2)) {
               const uint32_t base = sA_u + uint32_t(st.i) * kStage;
               uint4 r[4];
 #pragma unroll
@@ -602,7 +604,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
               for (int i = 0; i < 4; ++i)
                 if (ok[i]) ptx::sts128(base + off[i], r[i]);  // out-of-image pixels keep TMA's zero fill
             }
-            ptx::fence_proxy_async_smem();
+            if (!(P.ablate & 16)) ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&a_full[st.i]);
             if ((aw & 7) == 0 && lane == 0) STRACE(2, st.w * P.SA + st.i);
@@ -650,6 +652,296 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
   if (warp == 2) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ two rows per stage
+// Dense-block layers (pre-activated input; 3x3 in the row-fold form or 1x1) with TWO image rows per pipeline stage.
+// Every hand-off in this pipeline (TMA issue, raw_full -> workers, a_full -> MMA, commits, acc_done -> epilogue,
+// acc_free -> MMA) is a single-warp latency of 150-200 cycles, and with one row per stage those hand-offs alone cost
+// ~930 cycles per row (measured by ablation: all arithmetic, MMAs, TMEM traffic and stores removed).  Here one stage is
+// 32 KB = rows (j, j+1) of the strip, accumulator rows are signalled and recycled in pairs, and the two epilogue groups
+// each own one row of the pair — half the hand-offs per row, same data path.
+template <int FOLD, int EPI>
+__global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_constant__ CUtensorMap tmapA, const SParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kStage2 = 2 * kStage;
+  uint8_t* sA = smem;
+  uint8_t* sW = sA + size_t(P.SA) * kStage2 + 1024;
+  float* s_pre_s = reinterpret_cast<float*>(sW + P.wbytes);
+  float* s_pre_t = s_pre_s + P.nchunks * 64;
+  float* s_bias = s_pre_t + P.nchunks * 64;
+
+  __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], raw_full[kMaxSA], acc_done[kMaxR / 2], acc_free[kMaxR / 2], w_full;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr bool RFOLD = FOLD == 4;
+  constexpr int PAD = RFOLD ? 1 : 0;
+  constexpr int kEpiWarps = 8, kWorkWarp0 = kEpiWarp0 + kEpiWarps;
+
+  if (tid == 0) {
+    for (int i = 0; i < kMaxSA; ++i) {
+      ptx::mbar_init(&a_full[i], 8);
+      ptx::mbar_init(&a_empty[i], 1);
+      ptx::mbar_init(&raw_full[i], 1);
+    }
+    for (int i = 0; i < kMaxR / 2; ++i) {
+      ptx::mbar_init(&acc_done[i], 1);
+      ptx::mbar_init(&acc_free[i], 8);
+    }
+    ptx::mbar_init(&w_full, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&tmapA);
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(&tmem_base_s, 512);
+    ptx::tmem_relinquish();
+  }
+  for (int i = tid; i < P.nchunks * 64; i += blockDim.x) {
+    const bool ok = i < P.Cin;
+    s_pre_s[i] = ok ? P.pre_s[i] : 0.f;
+    s_pre_t[i] = ok ? P.pre_t[i] : 0.f;
+  }
+  for (int i = tid; i < P.NT; i += blockDim.x) s_bias[i] = P.bias[i];
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  if (PAD && warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {  // ring accumulators start at zero
+    const uint32_t lb = tmem_base + (uint32_t((warp & 3) * 32) << 16);
+    for (int c = 0; c < 512; c += 16) ptx::tmem_st16_zero(lb + c);
+    ptx::tmem_wait_st();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+
+  if (warp == 0) {
+    // ============================================================ producer
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(&w_full, P.wbytes);
+      for (uint32_t off = 0; off < P.wbytes; off += 32768)
+        ptx::bulk_g2s(sW + off, P.wpack + off, min(32768u, P.wbytes - off), &w_full);
+    }
+    __syncwarp();
+    Ring st;
+    for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+      const Item it = decode_item(P, item);
+      const int npairs = (it.h1 - it.h0 + 2 * PAD + 1) >> 1;
+      for (int pp = 0; pp < npairs; ++pp) {
+        const int j = it.h0 - PAD + 2 * pp;  // rows j, j+1: outside the image -> zero filled by TMA
+        for (int c = 0; c < P.nchunks; ++c) {
+          ptx::mbar_wait(&a_empty[st.i], (st.w & 1) ^ 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&raw_full[st.i], kStage2);
+            ptx::tma_load_4d(sA + size_t(st.i) * kStage2, &tmapA, c * 64, it.w0 - PAD, j, it.n, &raw_full[st.i]);
+          }
+          __syncwarp();
+          st.step(P.SA);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    const uint32_t idesc = ptx::umma_idesc_bf16(128, P.NMMA);
+    const uint64_t desc_hi = ptx::umma_desc_sw128(0, 1024) & 0xffffffff00000000ull;
+    const uint32_t flags = uint32_t(ptx::umma_desc_sw128(0, 1024) & 0xffffffffull);
+    const uint32_t a_base = flags | ((ptx::smem_u32(sA) & 0x3FFFFu) >> 4);
+    const uint32_t b_base = flags | ((ptx::smem_u32(sW) & 0x3FFFFu) >> 4);
+    const uint32_t blk16 = uint32_t(P.NMMA) * 8u;
+    const int klast = min(4, (P.Cin - (P.nchunks - 1) * 64 + 15) >> 4);
+    Ring st, dr, fr;  // stage; first accumulator row of the pair; newest accumulator row pair the input pair touches
+    fr.add(2 * PAD, P.R);
+    ptx::mbar_wait(&w_full, 0);
+    for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+      const Item it = decode_item(P, item);
+      const int npairs = (it.h1 - it.h0 + 2 * PAD + 1) >> 1;
+      for (int pp = 0; pp < npairs; ++pp) {
+        if (fr.w > 0) ptx::mbar_wait(&acc_free[fr.i >> 1], (fr.w - 1) & 1);
+        ptx::tc_fence_after_sync();
+        uint32_t b0 = b_base;
+        for (int c = 0; c < P.nchunks; ++c) {
+          const int ksteps = c == P.nchunks - 1 ? klast : 4;
+          ptx::mbar_wait(&a_full[st.i], st.w & 1);
+          ptx::tc_fence_after_sync();
+          const uint32_t a0 = a_base + uint32_t(st.i) * (kStage2 >> 4);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const uint32_t dc = tmem_base + uint32_t((dr.i + r) * P.SW);  // dr.i is even and R is even: no wrap
+              const uint32_t ar = a0 + uint32_t(r) * (kStage >> 4);
+              if (RFOLD) {
+#pragma unroll
+                for (int s = 0; s < 3; ++s)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (k < ksteps)
+                      ptx::umma_bf16(dc, desc_hi | (ar + uint32_t(8 * s + 2 * k)), desc_hi | (b0 + uint32_t(s) * blk16 + uint32_t(2 * k)), idesc, 1u);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (k < ksteps)
+                    ptx::umma_bf16(dc, desc_hi | (ar + uint32_t(2 * k)), desc_hi | (b0 + uint32_t(2 * k)), idesc, (c | k) != 0 ? 1u : 0u);
+              }
+            }
+            ptx::umma_commit(&a_empty[st.i]);
+          }
+          __syncwarp();
+          st.step(P.SA);
+          b0 += RFOLD ? 3u * blk16 : blk16;
+        }
+        if (ptx::elect_one()) ptx::umma_commit(&acc_done[dr.i >> 1]);
+        __syncwarp();
+        dr.add(2, P.R);
+        fr.add(2, P.R);
+      }
+      if (PAD) {  // the trailing accumulator-row pair of the segment receives no further input
+        if (ptx::elect_one()) ptx::umma_commit(&acc_done[dr.i >> 1]);
+        __syncwarp();
+        dr.add(2, P.R);
+        fr.add(2, P.R);
+      }
+    }
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
+    // ============================================================ epilogue: group eg owns row (pair start + eg)
+    const int eg = (warp - kEpiWarp0) >> 2, q = warp & 3;
+    const uint32_t lb = tmem_base + (uint32_t(q * 32) << 16);
+    const int px = q * 32 + lane;
+    Ring ar;
+    for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+      const Item it = decode_item(P, item);
+      const int n_acc_pairs = ((it.h1 - it.h0 + 2 * PAD + 1) >> 1) + PAD;
+      const int col = it.w0 + px;
+      const bool col_ok = px < P.TW && col < P.W;
+      int i = it.h0 - 2 * PAD + eg;
+      const size_t row_elems = EPI == kSNchwOut ? size_t(P.W) : size_t(P.W) * P.out_ld;
+      bf16* o_b = nullptr;
+      float* o_f = nullptr;
+      if (EPI == kSNchwOut) o_f = P.out_nchw + (size_t(it.n) * P.Cout * P.H + i) * P.W + col;
+      else o_b = P.out + ((size_t(it.n) * P.H + i) * P.W + col) * P.out_ld;
+      Ring pr = ar;
+      for (int pp = 0; pp < n_acc_pairs; ++pp) {
+        const int pslot = pr.i >> 1, slot = pr.i + eg;
+        ptx::mbar_wait(&acc_done[pslot], pr.w & 1);
+        ptx::tc_fence_after_sync();
+        const bool row_ok = i >= it.h0 && i < it.h1;
+        const bool shadow = PAD && slot < 2;
+        const uint32_t tm = lb + uint32_t(slot * P.SW), ts = lb + uint32_t((P.R + slot) * P.SW);
+        for (int c0 = 0; c0 < P.NT; c0 += 8) {
+          uint32_t v[8];
+          if (row_ok) {
+            ptx::tmem_ld8(tm + c0, v);
+            if (shadow) {
+              uint32_t v2[8];
+              ptx::tmem_ld8(ts + c0, v2);
+              ptx::tmem_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(v2[e]));
+            } else {
+              ptx::tmem_wait_ld();
+            }
+          }
+          if (PAD) {
+            ptx::tmem_st8_zero(tm + c0);
+            if (shadow) ptx::tmem_st8_zero(ts + c0);
+          }
+          if (row_ok && col_ok) {
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0), b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 4);
+            const float f[8] = {__uint_as_float(v[0]) + b0.x, __uint_as_float(v[1]) + b0.y, __uint_as_float(v[2]) + b0.z,
+                                __uint_as_float(v[3]) + b0.w, __uint_as_float(v[4]) + b1.x, __uint_as_float(v[5]) + b1.y,
+                                __uint_as_float(v[6]) + b1.z, __uint_as_float(v[7]) + b1.w};
+            if (EPI == kSNchwOut) {
+              const size_t plane = size_t(P.H) * P.W;
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (c0 + e < P.Cout) o_f[size_t(c0 + e) * plane] = P.sigmoid ? 1.0f / (1.0f + __expf(-f[e])) : f[e];
+            } else if (c0 < P.Cout) {  // channel slices are padded to multiples of 8
+              *reinterpret_cast<uint4*>(o_b + c0) = make_uint4(bf2(f[0], f[1]), bf2(f[2], f[3]), bf2(f[4], f[5]), bf2(f[6], f[7]));
+            }
+          }
+        }
+        if (PAD) ptx::tmem_wait_st();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&acc_free[pslot]);
+        pr.add(2, P.R);
+        i += 2;
+        if (EPI == kSNchwOut) o_f += 2 * row_elems; else o_b += 2 * row_elems;
+      }
+      ar.jump(2 * n_acc_pairs, P.R);
+    }
+  } else if (warp >= kWorkWarp0) {
+    // ============================================================ pre-activation workers (two groups alternate stages)
+    const int aw = warp - kWorkWarp0;
+    const int grp = aw >> 3, t = (aw & 7) * 32 + lane, u = t & 7, qb = t >> 3;
+    const uint32_t sA_u = ptx::smem_u32(sA);
+    uint32_t off[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) off[i] = ptx::sw128_offset(uint32_t(qb + 32 * i), uint32_t(u));
+    __nv_bfloat162 sc[4], sh[4];
+    int cached_c = -1;
+    Ring st;
+    int turn = 0;
+    for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+      const Item it = decode_item(P, item);
+      bool ok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int col = it.w0 - PAD + qb + 32 * i;
+        ok[i] = col >= 0 && col < P.W;
+      }
+      const int npairs = (it.h1 - it.h0 + 2 * PAD + 1) >> 1;
+      for (int pp = 0; pp < npairs; ++pp) {
+        const int j = it.h0 - PAD + 2 * pp;
+        for (int c = 0; c < P.nchunks; ++c, turn ^= 1, st.step(P.SA)) {
+          if (turn != grp) continue;
+          if (c != cached_c) {
+            const float4 fs0 = *reinterpret_cast<const float4*>(s_pre_s + c * 64 + u * 8);
+            const float4 fs1 = *reinterpret_cast<const float4*>(s_pre_s + c * 64 + u * 8 + 4);
+            const float4 ft0 = *reinterpret_cast<const float4*>(s_pre_t + c * 64 + u * 8);
+            const float4 ft1 = *reinterpret_cast<const float4*>(s_pre_t + c * 64 + u * 8 + 4);
+            sc[0] = __floats2bfloat162_rn(fs0.x, fs0.y); sc[1] = __floats2bfloat162_rn(fs0.z, fs0.w);
+            sc[2] = __floats2bfloat162_rn(fs1.x, fs1.y); sc[3] = __floats2bfloat162_rn(fs1.z, fs1.w);
+            sh[0] = __floats2bfloat162_rn(ft0.x, ft0.y); sh[1] = __floats2bfloat162_rn(ft0.z, ft0.w);
+            sh[2] = __floats2bfloat162_rn(ft1.x, ft1.y); sh[3] = __floats2bfloat162_rn(ft1.z, ft1.w);
+            cached_c = c;
+          }
+          const bool active = u * 8 < min(64, P.Cin - c * 64);
+          ptx::mbar_wait(&raw_full[st.i], st.w & 1);
+          if (active) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              if (j + r < 0 || j + r >= P.H) continue;  // rows outside the image keep TMA's zero fill (padding after activation)
+              const uint32_t base = sA_u + uint32_t(st.i) * kStage2 + uint32_t(r) * kStage;
+              uint4 x[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) x[i] = ptx::lds128(base + off[i]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162* v = reinterpret_cast<__nv_bfloat162*>(&x[i]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = __hfma2_relu(v[e], sc[e], sh[e]);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (ok[i]) ptx::sts128(base + off[i], x[i]);
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&a_full[st.i]);
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -855,8 +1147,18 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
     const int tail2 = 2 * pk.nchunks * 64 * 4 + 64 * 4 + 256;
     dual = wb > 0 && (kSmemLimit2 - 1024 - int(wb) - tail2) / kStage >= 3;
   }
+  // Two rows per stage (conv_stream2_kernel): default for the 1x1 transition layers (measured 10-15 % faster there);
+  // CDAN_RPS=2 also routes the 3x3 dense layers through it (row-fold form; measured ~5 % slower than the nine-tap fold),
+  // CDAN_RPS=1 disables it.
+  static const int rps_env = getenv("CDAN_RPS") ? atoi(getenv("CDAN_RPS")) : 0;
+  bool rps2 = false;
+  if (rps_env != 1 && (fold == 1 || rps_env == 2) && !dual && in_mode == kSPro && !d.pool) {
+    const size_t wb = fold == 3 ? (pk.d_wr && !d.out_nchw ? pk.rfold_bytes : 0) : pk.pass_bytes;
+    const int tail2 = 2 * pk.nchunks * 64 * 4 + 128 * 4 + 256;
+    rps2 = wb > 0 && (kSmemLimit - 1024 - int(wb) - tail2) / (2 * kStage) >= 4;
+  }
   static const char* dense_form = getenv("CDAN_DENSE_FORM");  // "rfold" | "shift" (A/B switch), default per layer
-  const bool rfold = fold == 3 && in_mode == kSPro && pk.d_wr && !d.out_nchw && (dual || (dense_form && !strcmp(dense_form, "rfold")));  // measured equal or slightly slower than the nine-tap fold on B200
+  const bool rfold = fold == 3 && in_mode == kSPro && pk.d_wr && !d.out_nchw && (dual || rps2 || (dense_form && !strcmp(dense_form, "rfold")));  // measured equal or slightly slower than the nine-tap fold on B200
   const bool shift = (fold == 3 && in_mode == kSPro && !rfold) || fold9;
   P.NMMA = shift ? 9 * P.NT : (wide ? P.NT : fold * P.NT);  // rfold: 3 * 16
   P.SW = shift ? 3 * P.NT : P.NT;
@@ -878,9 +1180,16 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   P.out_ld = d.out_ld; P.out_nchw = d.out_nchw;
   P.wbytes = uint32_t(kfold ? size_t(192) * 128 : (wide ? pk.wide_bytes : (rfold ? pk.rfold_bytes : pk.pass_bytes)));
   const int tail = 2 * P.nchunks * 64 * 4 + std::max(P.NT, 64) * 4 + 256 + (kfold ? kRawStages * kRawFloats * 4 + 128 : 0);
-  P.SA = std::min(kMaxSA, ((dual ? kSmemLimit2 : kSmemLimit) - 1024 - int(P.wbytes) - tail) / kStage);
+  const int stage_bytes = rps2 ? 2 * kStage : kStage;
+  P.SA = std::min(kMaxSA, ((dual ? kSmemLimit2 : kSmemLimit) - 1024 - int(P.wbytes) - tail) / stage_bytes);
+  // The two worker groups take alternate stages: with an even stage count every ring slot always belongs to the same
+  // group.  (With an odd count a group could test a slot's mbarrier parity a full phase ahead of the last phase it
+  // observed there — parity waits then return a false positive and the pipeline desynchronises.)
+  if (in_mode == kSPro) P.SA &= ~1;
+  static const int sa_cap = getenv("CDAN_SA_MAX") ? atoi(getenv("CDAN_SA_MAX")) : kMaxSA;
+  P.SA = std::min(P.SA, std::max(3, sa_cap));
   if (P.SA < 3) return fail("conv_stream: weights leave no room for the activation pipeline");
-  const int smem_bytes = P.SA * kStage + 1024 + int(P.wbytes) + tail + 1024;
+  const int smem_bytes = P.SA * stage_bytes + 1024 + int(P.wbytes) + tail + 1024;
 
   CUtensorMap tmap;
   std::memset(&tmap, 0, sizeof(tmap));
@@ -890,7 +1199,7 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
     if (reinterpret_cast<uintptr_t>(d.in) % 16 != 0) return fail("conv_stream: input pointer must be 16-byte aligned");
     cuuint64_t gdim[4] = {cuuint64_t(d.Cin), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.N)};
     cuuint64_t gstr[3] = {cuuint64_t(d.in_ld) * 2, cuuint64_t(d.W) * d.in_ld * 2, cuuint64_t(d.H) * d.W * d.in_ld * 2};
-    cuuint32_t box[4] = {64, cuuint32_t(shift ? 32 : 128), 1, 1};
+    cuuint32_t box[4] = {64, cuuint32_t(shift ? 32 : 128), cuuint32_t(rps2 ? 2 : 1), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.in), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -923,8 +1232,10 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
     P.trace = d_trace;
   }
 #endif
+  static const int ablate = getenv("CDAN_ABLATE") ? atoi(getenv("CDAN_ABLATE")) : 0;
+  P.ablate = ablate;
   const int grid = std::min(P.nitems, dual ? 2 * sms : sms);
-  const int threads = 32 * (kEpiWarp0 + epi_warps(dual ? kSPro2 : in_mode) + work_warps(dual ? kSPro2 : in_mode));
+  const int threads = rps2 ? 896 : 32 * (kEpiWarp0 + epi_warps(dual ? kSPro2 : in_mode) + work_warps(dual ? kSPro2 : in_mode));
   const int npass = kfold ? 1 : (wide ? pk.npass_w : pk.npass);
   for (int pass = 0; pass < npass; ++pass) {
     P.wpack = kfold ? pk.d_wk : (wide ? pk.d_ww + size_t(pass) * pk.wide_bytes : (rfold ? pk.d_wr : pk.d_w + size_t(pass) * pk.pass_bytes));
@@ -938,7 +1249,10 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
       return 0;
     };
     int rc;
-    if (kfold) rc = d.pool ? launch(conv_stream_kernel<kSNchw, 3, kSPool>) : launch(conv_stream_kernel<kSNchw, 3, kSStore>);
+    if (rps2) {
+      if (fold == 3) rc = launch(conv_stream2_kernel<4, kSStore>);
+      else rc = d.out_nchw ? launch(conv_stream2_kernel<1, kSNchwOut>) : launch(conv_stream2_kernel<1, kSStore>);
+    } else if (kfold) rc = d.pool ? launch(conv_stream_kernel<kSNchw, 3, kSPool>) : launch(conv_stream_kernel<kSNchw, 3, kSStore>);
     else if (fold == 3) {
       if (d.out_nchw) rc = in_mode == kSPro ? launch(conv_stream_kernel<kSPro, 3, kSNchwOut>) : launch(conv_stream_kernel<kSTma, 3, kSNchwOut>);
       else if (in_mode == kSPro && dual) rc = launch(conv_stream_kernel<kSPro2, 4, kSStore>);
