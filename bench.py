@@ -7,8 +7,10 @@ A "step" is one eval-mode CDAN forward over one synthetic batch.  Workload at ev
 PER GPU (BASELINE config C3's batch, the configuration the metric is quoted on; batch-sharded, no collective ->
 weak scaling).  `value` = megapixels/s with inputs resident in HBM, device-timed (CUDA events, max over ranks);
 `e2e` = the same through the host-buffer C-ABI call (pinned host input -> H2D -> forward -> D2H) per step.
-`roofline` is for the dominant kernel (the tcgen05 convolution: all 28 launches of one step) against the measured
-bf16 peak; `cpu_baseline` is the CPU oracle port timed on this box's host cores on a bounded sample.
+`roofline` is for the tcgen05 convolutions (conv_stream_kernel + conv_umma_kernel, all conv launches of one step) against
+the measured bf16 peak; `roofline_dense` is for the single heaviest kernel, conv_stream_kernel<1,3,0> (the 16 dense-block
+3x3 layers, ~39 % of the step), against the measured HBM bandwidth; `cpu_baseline` is the CPU oracle port timed on this
+box's host cores on a bounded sample.
 Inputs (796 MB per step) and activations are far larger than the 126 MB L2, so no explicit L2 flush is needed.
 `--impl reference` times the reference algorithm's CPU restatement (oracle/, the reference itself is a Python tree that
 does not travel to the GPU box) on all host threads.
@@ -35,6 +37,14 @@ import torch  # noqa: E402
 METRIC = "megapixels/sec CDAN fwd (1080p bf16)"
 UNIT = "MP/s"
 FLOP_PER_PIXEL = 252770  # algorithmic conv FLOPs (2*MAC, unpadded), SURVEY 8(d) / BASELINE.md 3
+# Dense-block 3x3 layers: logical input channels and resolution divisor; algorithmic HBM bytes per layer
+# and output pixel in bf16 = 2 * (Cin + 16): read the concat prefix once, write the 16 new channels once.
+DENSE3X3 = {f"{blk}.layers.{l}": (c0 + 16 * l, div)
+            for blk, c0, div in (("encoder.dense1", 64, 2), ("encoder.dense2", 128, 4), ("encoder.dense3", 256, 8),
+                                 ("decoder.final_dense", 3, 1)) for l in range(4)}
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the 16 launches of one 32 x 1080p step from the
+# `ncu --set full` capture summarised in profiles/r01_dense3x3_ncu.md; None until that capture exists for this build.
+DENSE3X3_NCU_TRAFFIC_BYTES = None
 
 
 def measured_peaks():
@@ -268,7 +278,7 @@ def main():
                     "d2h_bytes_per_step": n * 3 * h * w * 4, "ms_per_step": e2e_s * 1e3,
                     "api": "Plan.forward_host -> cdan_forward_host (pinned fp32 NCHW host buffers)"},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "tensor", "kernel": "conv_umma_kernel (all conv launches of a step)",
+            "roofline": {"bound": "tensor", "kernel": "tcgen05 convolutions: conv_stream_kernel + conv_umma_kernel (all conv launches of a step)",
                          "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tensor"], "traffic": None, "peak_source": peaks["source"] + " (sustained)",
                          "launches_per_step": conv_launches, "kernel_ms_per_step": conv_ms,
@@ -280,6 +290,16 @@ def main():
                               "kernel_ms_per_step": cbam_ms, "note": "achieved = compulsory 144 B/px over the 4 CBAM sites"},
             "glue_ms_per_step": glue_ms,
         }
+        dense_ms = sum(v[0] for k, v in spans.items() if k.split("|")[1] in DENSE3X3) / args.steps
+        dense_bytes = sum(2.0 * (cin + 16) * n * (h // div) * (w // div) for cin, div in DENSE3X3.values())
+        if dense_ms > 0:
+            gbs = dense_bytes / (dense_ms * 1e-3) / 1e9
+            line["roofline_dense"] = {
+                "bound": "hbm", "kernel": "conv_stream_kernel<1,3,0> (16 dense-block 3x3 launches of a step)",
+                "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                "traffic": DENSE3X3_NCU_TRAFFIC_BYTES if (n, h, w) == (32, 1080, 1920) else None,
+                "algorithmic_bytes_per_step": dense_bytes, "kernel_ms_per_step": dense_ms,
+                "kernel_share_of_step": dense_ms / ms_step if ms_step else None, "launches_per_step": len(DENSE3X3)}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             mp_s, sample, _ = cpu_oracle_rate(h, w, args.cpu_budget, threads)

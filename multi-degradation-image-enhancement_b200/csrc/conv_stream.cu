@@ -129,6 +129,26 @@ struct Ring {
   __device__ __forceinline__ void jump(int k, int n) { i += k; const int d = i / n; w += d; i -= d * n; }  // once per item
 };
 
+// Accumulator-ring bookkeeping.  A row's ring slot is a function of its ABSOLUTE image row (slot = (row + 2*PAD) mod R),
+// not of a running counter: which slot a row lands in decides the association of its three vertical-tap partial sums
+// (slots 0 and 1 are completed through the shadow slots), so tying it to the image row makes results independent of the
+// batch size and of how the image is cut into segments.  Segments therefore start at arbitrary ring positions, and the
+// mbarrier phase of every slot is tracked individually: bit s of `par` = parity of the next completion to wait for.
+struct SlotPhases {
+  uint32_t par = 0, used = 0;
+  // consumer side of a barrier that is armed once per use of the slot
+  __device__ __forceinline__ void wait(uint64_t* bars, int s) {
+    ptx::mbar_wait(&bars[s], (par >> s) & 1u);
+    par ^= 1u << s;
+  }
+  __device__ __forceinline__ void skip(int s) { par ^= 1u << s; }  // a use observed by someone else
+  // producer side: before the first write of a new use, wait until the previous use (if any) was drained
+  __device__ __forceinline__ void claim(uint64_t* free_bars, int s) {
+    if ((used >> s) & 1u) wait(free_bars, s);
+    used |= 1u << s;
+  }
+};
+
 template <int IN, int FOLD, int EPI>
 __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(IN)), IN == 3 ? 2 : 1) conv_stream_kernel(const __grid_constant__ CUtensorMap tmapA, const SParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -263,19 +283,27 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
       const uint32_t b_base = flags | ((ptx::smem_u32(sW) & 0x3FFFFu) >> 4);
       const uint32_t blk16 = uint32_t(P.NMMA) * 8u;  // one [NMMA x 128 B] weight block in 16-byte units
       const int klast = IN == kSNchw ? 1 : min(4, (P.Cin - (P.nchunks - 1) * 64 + 15) >> 4);
-      Ring st;   // A stage
-      Ring dr;   // accumulator row this input row's window starts at (G + jj)
-      Ring fr;   // newest accumulator row it touches (G + jj + 2*PAD): must have been drained R rows ago
-      fr.add(2 * PAD, P.R);
+      Ring st;        // A stage
+      Ring dr;        // ring slot of the accumulator row this input row's window starts at
+      SlotPhases fp;  // acc_free phases
       ptx::mbar_wait(&w_full, 0);
       for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
         const Item it = decode_item(P, item);
         const int n_in = it.h1 - it.h0 + 2 * PAD;
+        dr.i = it.h0 % P.R;  // accumulator row 0 of the segment = image row h0 - 2*PAD
+        if (PAD) {           // the first input row also opens the segment's first two accumulator rows
+          fp.claim(acc_free, dr.i);
+          fp.claim(acc_free, dr.i + 1 == P.R ? 0 : dr.i + 1);
+        }
         for (int jj = 0; jj < n_in; ++jj) {
           const int j = it.h0 - PAD + jj;
-          if (fr.w > 0) ptx::mbar_wait(&acc_free[fr.i], (fr.w - 1) & 1);
+          {
+            int newest = dr.i + 2 * PAD;  // newest accumulator row this input row touches
+            if (newest >= P.R) newest -= P.R;
+            fp.claim(acc_free, newest);
+          }
           ptx::tc_fence_after_sync();
-          if (lane == 0) STRACE(7, dr.w * P.R + dr.i);
+          if (lane == 0) STRACE(7, dr.i);
           if (j >= 0 && j < P.H) {
             const uint32_t dcol = tmem_base + uint32_t(dr.i * P.SW);
             uint32_t b0 = b_base;
@@ -331,7 +359,6 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
           if (ptx::elect_one()) ptx::umma_commit(&acc_done[dr.i]);
           __syncwarp();
           dr.step(P.R);
-          fr.step(P.R);
         }
         if (PAD) {  // the two trailing accumulator rows of the segment receive no further input
           if (ptx::elect_one()) ptx::umma_commit(&acc_done[dr.i]);
@@ -340,7 +367,6 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
           if (ptx::elect_one()) ptx::umma_commit(&acc_done[dr.i]);
           __syncwarp();
           dr.step(P.R);
-          fr.add(2, P.R);
         }
       }
     }
@@ -349,16 +375,19 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
     const int eg = (warp - kEpiWarp0) >> 2, q = warp & 3;
     const uint32_t lb = tmem_base + (uint32_t(q * 32) << 16);
     const int px = q * 32 + lane;
-    Ring ar;  // first accumulator row of the current item
-    int apar = 0;  // parity of the running accumulator-row index A (rows alternate between the epilogue groups)
+    SlotPhases dp;  // acc_done phases
+    int pairs_seen = 0;  // running count of pooled row pairs (they alternate between the epilogue groups)
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const Item it = decode_item(P, item);
       const int n_acc = it.h1 - it.h0 + 4 * PAD;
       const int col = SHIFT ? it.w0 - 1 + 30 * q + lane : it.w0 + px;
       const bool col_ok = SHIFT ? (lane >= 1 && lane <= 30 && col < P.W && col < it.w0 + P.TW) : (px < P.TW && col < P.W);
       if (EPI != kSPool) {
-        const int ii0 = kEG == 2 ? (eg ^ (apar & 1)) : 0;
-        Ring sr = ar;
+        // segments start at even image rows and R is even: accumulator row ii sits in a slot of parity (ii & 1), so a
+        // slot always belongs to the same epilogue group
+        const int ii0 = kEG == 2 ? eg : 0;
+        Ring sr;
+        sr.i = it.h0 % P.R;
         sr.add(ii0, P.R);
         int i = it.h0 - 2 * PAD + ii0;
         // output address of (n, i, col): advanced by kEG rows per step
@@ -369,9 +398,9 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
         else o_b = P.out + ((size_t(it.n) * P.H + i) * P.W + col) * P.out_ld;
         for (int ii = ii0; ii < n_acc; ii += kEG) {
           const int slot = sr.i;
-          ptx::mbar_wait(&acc_done[slot], sr.w & 1);
+          dp.wait(acc_done, slot);
           ptx::tc_fence_after_sync();
-          if (q == 0 && lane == 0) STRACE(5, sr.w * P.R + sr.i);
+          if (q == 0 && lane == 0) STRACE(5, sr.i);
           const bool row_ok = i >= it.h0 && i < it.h1 && !(P.ablate & 8);
           const bool shadow = PAD && !WIDE && slot < 2;
           const uint32_t tm = lb + uint32_t(slot * P.SW), ts = lb + uint32_t((P.R + slot) * P.SW);
@@ -455,7 +484,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
           ptx::tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&acc_free[slot]);
-          if (q == 0 && lane == 0) STRACE(6, sr.w * P.R + sr.i);
+          if (q == 0 && lane == 0) STRACE(6, sr.i);
           sr.add(kEG, P.R);
           i += kEG;
           if (EPI == kSNchwOut) o_f += kEG * row_elems; else o_b += kEG * row_elems;
@@ -463,16 +492,21 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
       } else {
         // 2x2 max-pool: accumulator rows (a, a+1) <-> image rows (i, i+1), i even; horizontal partner = lane ^ 1.
         // Row pairs alternate between the two epilogue groups.  (A is even at every item start: segments are even.)
-        const int pp0 = kEG == 2 ? (eg ^ (apar >> 1)) : 0;  // first pair index of this group
-        Ring sr = ar;
-        sr.add(2 * pp0, P.R);
-        int i = it.h0 - 2 * PAD + 2 * pp0;
-        for (int ii = 2 * pp0; ii < n_acc; ii += 2 * kEG) {
-          const int sl0 = sr.i, sl1 = sr.i + 1;  // R is even, so a pair never straddles the ring end
-          ptx::mbar_wait(&acc_done[sl0], sr.w & 1);
-          ptx::mbar_wait(&acc_done[sl1], sr.w & 1);
+        // every group walks all pairs (to keep every slot's phase bit current) but only drains its own
+        Ring sr;
+        sr.i = it.h0 % P.R;
+        int i = it.h0 - 2 * PAD;
+        for (int ii = 0; ii < n_acc; ii += 2, ++pairs_seen, sr.add(2, P.R), i += 2) {
+          const int sl0 = sr.i, sl1 = sr.i + 1;  // h0 and R are even, so a pair never straddles the ring end
+          if (kEG == 2 && (pairs_seen & 1) != eg) {
+            dp.skip(sl0);
+            dp.skip(sl1);
+            continue;
+          }
+          dp.wait(acc_done, sl0);
+          dp.wait(acc_done, sl1);
           ptx::tc_fence_after_sync();
-          if (q == 0 && lane == 0) STRACE(5, (sr.w * P.R + sr.i) >> 1);
+          if (q == 0 && lane == 0) STRACE(5, sr.i >> 1);
           const bool row_ok = i >= it.h0 && i < it.h1;
           const bool sh0 = !WIDE && sl0 < 2, sh1 = !WIDE && sl1 < 2;
           const uint32_t t0 = lb + uint32_t(sl0 * P.NT), t1 = lb + uint32_t(sl1 * P.NT);
@@ -534,13 +568,9 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
             ptx::mbar_arrive(&acc_free[sl0]);
             ptx::mbar_arrive(&acc_free[sl1]);
           }
-          if (q == 0 && lane == 0) STRACE(6, (sr.w * P.R + sr.i) >> 1);
-          sr.add(2 * kEG, P.R);
-          i += 2 * kEG;
+          if (q == 0 && lane == 0) STRACE(6, sr.i >> 1);
         }
       }
-      ar.jump(n_acc, P.R);
-      apar = (apar + n_acc) & 3;
     }
   } else if (warp >= kWorkWarp0) {
     // ============================================================ A-stage workers
@@ -752,14 +782,20 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
     const uint32_t b_base = flags | ((ptx::smem_u32(sW) & 0x3FFFFu) >> 4);
     const uint32_t blk16 = uint32_t(P.NMMA) * 8u;
     const int klast = min(4, (P.Cin - (P.nchunks - 1) * 64 + 15) >> 4);
-    Ring st, dr, fr;  // stage; first accumulator row of the pair; newest accumulator row pair the input pair touches
-    fr.add(2 * PAD, P.R);
+    Ring st, dr;    // stage; ring slot of the first accumulator row of the current pair (tied to the absolute image row)
+    SlotPhases fp;  // acc_free phases, one bit per slot pair
     ptx::mbar_wait(&w_full, 0);
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const Item it = decode_item(P, item);
       const int npairs = (it.h1 - it.h0 + 2 * PAD + 1) >> 1;
+      dr.i = it.h0 % P.R;  // even: segments start at even rows, R is even
+      if (PAD) fp.claim(acc_free, dr.i >> 1);  // the first input pair also opens the segment's first accumulator pair
       for (int pp = 0; pp < npairs; ++pp) {
-        if (fr.w > 0) ptx::mbar_wait(&acc_free[fr.i >> 1], (fr.w - 1) & 1);
+        {
+          int newest = dr.i + 2 * PAD;  // newest accumulator pair this input pair touches
+          if (newest >= P.R) newest -= P.R;
+          fp.claim(acc_free, newest >> 1);
+        }
         ptx::tc_fence_after_sync();
         uint32_t b0 = b_base;
         for (int c = 0; c < P.nchunks; ++c) {
@@ -795,13 +831,11 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
         if (ptx::elect_one()) ptx::umma_commit(&acc_done[dr.i >> 1]);
         __syncwarp();
         dr.add(2, P.R);
-        fr.add(2, P.R);
       }
       if (PAD) {  // the trailing accumulator-row pair of the segment receives no further input
         if (ptx::elect_one()) ptx::umma_commit(&acc_done[dr.i >> 1]);
         __syncwarp();
         dr.add(2, P.R);
-        fr.add(2, P.R);
       }
     }
   } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
@@ -809,7 +843,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
     const int eg = (warp - kEpiWarp0) >> 2, q = warp & 3;
     const uint32_t lb = tmem_base + (uint32_t(q * 32) << 16);
     const int px = q * 32 + lane;
-    Ring ar;
+    SlotPhases dp;  // acc_done phases, one bit per slot pair
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const Item it = decode_item(P, item);
       const int n_acc_pairs = ((it.h1 - it.h0 + 2 * PAD + 1) >> 1) + PAD;
@@ -821,10 +855,11 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
       float* o_f = nullptr;
       if (EPI == kSNchwOut) o_f = P.out_nchw + (size_t(it.n) * P.Cout * P.H + i) * P.W + col;
       else o_b = P.out + ((size_t(it.n) * P.H + i) * P.W + col) * P.out_ld;
-      Ring pr = ar;
+      Ring pr;
+      pr.i = it.h0 % P.R;
       for (int pp = 0; pp < n_acc_pairs; ++pp) {
         const int pslot = pr.i >> 1, slot = pr.i + eg;
-        ptx::mbar_wait(&acc_done[pslot], pr.w & 1);
+        dp.wait(acc_done, pslot);
         ptx::tc_fence_after_sync();
         const bool row_ok = i >= it.h0 && i < it.h1;
         const bool shadow = PAD && slot < 2;
@@ -870,7 +905,6 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
         i += 2;
         if (EPI == kSNchwOut) o_f += 2 * row_elems; else o_b += 2 * row_elems;
       }
-      ar.jump(2 * n_acc_pairs, P.R);
     }
   } else if (warp >= kWorkWarp0) {
     // ============================================================ pre-activation workers (two groups alternate stages)
@@ -1052,7 +1086,7 @@ int stream_pack_create(const float* w, const float* bias, int Cin, int Cout, int
   if (ks == 3) {  // wide form: per 64-channel pass nine [NTw x 64ch] blocks per K-chunk, resident in shared memory
     const int NTw = Cout <= 16 ? 16 : 64, npw = (Cout + NTw - 1) / NTw;
     const size_t block = size_t(NTw) * 128, bytes = size_t(p->nchunks) * 9 * block;
-    if (bytes <= 152 * 1024 && npw <= 2) {
+    if (bytes <= 152 * 1024 && npw <= 2) {  // conv3 in four passes measured no faster than the tile kernel
       std::vector<uint8_t> ww(bytes * npw, 0);
       for (int pass = 0; pass < npw; ++pass)
         for (int c = 0; c < p->nchunks; ++c)
@@ -1147,12 +1181,12 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
     const int tail2 = 2 * pk.nchunks * 64 * 4 + 64 * 4 + 256;
     dual = wb > 0 && (kSmemLimit2 - 1024 - int(wb) - tail2) / kStage >= 3;
   }
-  // Two rows per stage (conv_stream2_kernel): default for the 1x1 transition layers (measured 10-15 % faster there);
-  // CDAN_RPS=2 also routes the 3x3 dense layers through it (row-fold form; measured ~5 % slower than the nine-tap fold),
-  // CDAN_RPS=1 disables it.
-  static const int rps_env = getenv("CDAN_RPS") ? atoi(getenv("CDAN_RPS")) : 0;
+  // Two rows per stage (conv_stream2_kernel) is the default for all dense pre-activation layers (3x3 in the row-fold
+  // form): the MMA warp's per-iteration latency is on the critical path and is paid once per two rows.  CDAN_RPS=1
+  // selects the one-row kernel (nine-tap fold) instead.
+  static const int rps_env = getenv("CDAN_RPS") ? atoi(getenv("CDAN_RPS")) : 2;
   bool rps2 = false;
-  if (rps_env != 1 && (fold == 1 || rps_env == 2) && !dual && in_mode == kSPro && !d.pool) {
+  if (rps_env != 1 && !dual && in_mode == kSPro && !d.pool) {
     const size_t wb = fold == 3 ? (pk.d_wr && !d.out_nchw ? pk.rfold_bytes : 0) : pk.pass_bytes;
     const int tail2 = 2 * pk.nchunks * 64 * 4 + 128 * 4 + 256;
     rps2 = wb > 0 && (kSmemLimit - 1024 - int(wb) - tail2) / (2 * kStage) >= 4;
