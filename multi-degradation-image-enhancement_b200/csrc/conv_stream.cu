@@ -1084,7 +1084,8 @@ int stream_pack_create(const float* w, const float* bias, int Cin, int Cout, int
     }
   }
   if (ks == 3) {  // wide form: per 64-channel pass nine [NTw x 64ch] blocks per K-chunk, resident in shared memory
-    const int NTw = Cout <= 16 ? 16 : 64, npw = (Cout + NTw - 1) / NTw;
+    static const int ntw_big = getenv("CDAN_NTW") ? atoi(getenv("CDAN_NTW")) : 128;  // conv2: one N=128 pass (2.49 ms) beats two N=64 passes (2.82 ms)
+    const int NTw = Cout <= 16 ? 16 : (Cout > 64 ? ntw_big : 64), npw = (Cout + NTw - 1) / NTw;
     const size_t block = size_t(NTw) * 128, bytes = size_t(p->nchunks) * 9 * block;
     if (bytes <= 152 * 1024 && npw <= 2) {  // conv3 in four passes measured no faster than the tile kernel
       std::vector<uint8_t> ww(bytes * npw, 0);
