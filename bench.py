@@ -8,8 +8,8 @@ PER GPU (BASELINE config C3's batch, the configuration the metric is quoted on; 
 weak scaling).  `value` = megapixels/s with inputs resident in HBM, device-timed (CUDA events, max over ranks);
 `e2e` = the same through the host-buffer C-ABI call (pinned host input -> H2D -> forward -> D2H) per step.
 `roofline` is for the tcgen05 convolutions (conv_stream_kernel + conv_umma_kernel, all conv launches of one step) against
-the measured bf16 peak; `roofline_dense` is for the single heaviest kernel, conv_stream_kernel<1,3,0> (the 16 dense-block
-3x3 layers, ~39 % of the step), against the measured HBM bandwidth; `cpu_baseline` is the CPU oracle port timed on this
+the measured bf16 peak; `roofline_dense` is for the single heaviest kernel, conv_stream2_kernel<4,0> (the 16 dense-block
+3x3 layers, ~36 % of the step), against the measured HBM bandwidth; `cpu_baseline` is the CPU oracle port timed on this
 box's host cores on a bounded sample.
 Inputs (796 MB per step) and activations are far larger than the 126 MB L2, so no explicit L2 flush is needed.
 `--impl reference` times the reference algorithm's CPU restatement (oracle/, the reference itself is a Python tree that
@@ -42,9 +42,10 @@ FLOP_PER_PIXEL = 252770  # algorithmic conv FLOPs (2*MAC, unpadded), SURVEY 8(d)
 DENSE3X3 = {f"{blk}.layers.{l}": (c0 + 16 * l, div)
             for blk, c0, div in (("encoder.dense1", 64, 2), ("encoder.dense2", 128, 4), ("encoder.dense3", 256, 8),
                                  ("decoder.final_dense", 3, 1)) for l in range(4)}
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the 16 launches of one 32 x 1080p step from the
-# `ncu --set full` capture summarised in profiles/r01_dense3x3_ncu.md; None until that capture exists for this build.
-DENSE3X3_NCU_TRAFFIC_BYTES = None
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per 32 x 1080p step from the `ncu --set full` capture
+# summarised in profiles/r01_allconv_ncu.md: the 16 dense-block 3x3 launches, and all 29 convolution launches.
+DENSE3X3_NCU_TRAFFIC_BYTES = 58469929000
+ALLCONV_NCU_TRAFFIC_BYTES = 98357771000
 
 
 def measured_peaks():
@@ -278,9 +279,11 @@ def main():
                     "d2h_bytes_per_step": n * 3 * h * w * 4, "ms_per_step": e2e_s * 1e3,
                     "api": "Plan.forward_host -> cdan_forward_host (pinned fp32 NCHW host buffers)"},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "tensor", "kernel": "tcgen05 convolutions: conv_stream_kernel + conv_umma_kernel (all conv launches of a step)",
+            "roofline": {"bound": "tensor", "kernel": "tcgen05 convolutions: conv_stream2_kernel + conv_stream_kernel + conv_umma_kernel (all conv launches of a step)",
                          "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tensor"], "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+                         "frac": achieved / peaks["tensor"],
+                         "traffic": ALLCONV_NCU_TRAFFIC_BYTES if (n, h, w) == (32, 1080, 1920) else None,
+                         "peak_source": peaks["source"] + " (sustained)",
                          "launches_per_step": conv_launches, "kernel_ms_per_step": conv_ms,
                          "kernel_share_of_step": conv_ms / ms_step if ms_step else None,
                          "whole_step_frac": flops_step / (ms_step * 1e-3) / 1e12 / peaks["tensor"]},
@@ -295,7 +298,7 @@ def main():
         if dense_ms > 0:
             gbs = dense_bytes / (dense_ms * 1e-3) / 1e9
             line["roofline_dense"] = {
-                "bound": "hbm", "kernel": "conv_stream_kernel<1,3,0> (16 dense-block 3x3 launches of a step)",
+                "bound": "hbm", "kernel": "conv_stream2_kernel<4,0> (16 dense-block 3x3 launches of a step)",
                 "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                 "traffic": DENSE3X3_NCU_TRAFFIC_BYTES if (n, h, w) == (32, 1080, 1920) else None,
                 "algorithmic_bytes_per_step": dense_bytes, "kernel_ms_per_step": dense_ms,

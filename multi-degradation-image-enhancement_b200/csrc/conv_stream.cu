@@ -1238,7 +1238,9 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.in), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     d.Cin >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : (d.Cin >= 32 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE),
+                     // 128-byte L2 promotion only when every K-chunk is a full 128-byte line; otherwise 64 bytes (ncu: with
+                     // promotion NONE a 32-byte line still pulled 128 bytes from DRAM, with 64B it pulls 64)
+                     (d.Cin % 64 == 0 && !getenv("CDAN_PROMO64")) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("conv_stream: cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
   }
