@@ -18,6 +18,8 @@ struct ConvDesc {
   int ks = 3;               // 3 or 1
   const void* in = nullptr; // NHWC, storage type T
   int in_ld = 0;
+  size_t in_gstride = 0;    // bf16 tensor-core path only: if non-zero the input is GROUP-PLANAR — one dense plane
+                            // [N][H][W][16] per 16-channel group, planes `in_gstride` elements apart, in_ld = 16
   const float* in_nchw = nullptr;  // if set: planar fp32 input [N][Cin][H][W] (first layer), `in` unused
   const float* pre_scale = nullptr;
   const float* pre_shift = nullptr;

@@ -171,6 +171,7 @@ int launch(const ConvDesc& d, cudaStream_t stream) {
 
 int conv_simt_launch(const ConvDesc& d, DType dt, cudaStream_t stream) {
   if (d.ks != 1 && d.ks != 3) return fail("conv_simt: kernel size must be 1 or 3");
+  if (d.in_gstride) return fail("conv_simt: group-planar input is only implemented by the streaming tensor-core kernel");
   if (d.pool && ((d.H | d.W) & 1)) return fail("conv_simt: fused max-pool needs even H and W");
   if (d.CoutP % 4 != 0) return fail("conv_simt: packed Cout stride must be a multiple of 4");
   if (d.N > 65535) return fail("conv_simt: batch too large for one launch");

@@ -56,6 +56,7 @@ enum SEpi : int { kSStore = 0, kSPool = 1, kSNchwOut = 2 };
 
 constexpr int kStage = 16384;  // one input row: 128 pixels x 64 channels bf16
 constexpr int kMaxSA = 12;
+constexpr int kMaxSA2 = 16;  // two-row kernel (group-planar stages can be as small as 8 KB)
 // conv1 raw fp32 row ring: one stage = 3 channels x 136 pixels starting at column w0-4 (TMA needs the innermost start
 // coordinate 16-byte aligned; w0 is a multiple of 4), 2 KB per stage.
 constexpr int kRawStages = 8, kRawW = 136, kRawFloats = 512;
@@ -76,6 +77,7 @@ struct SParams {
   int R;         // ring slots (excluding the two shadow slots)
   int TW, strips, SEG, segs, nitems;
   int nchunks, nS, SA;
+  int stage_bytes;  // group-planar input only: bytes per two-row stage (8 KB per 16-channel group)
   int relu, sigmoid, Cout;
   uint32_t wbytes;
   const bf16* in;
@@ -692,18 +694,26 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
 // ~930 cycles per row (measured by ablation: all arithmetic, MMAs, TMEM traffic and stores removed).  Here one stage is
 // 32 KB = rows (j, j+1) of the strip, accumulator rows are signalled and recycled in pairs, and the two epilogue groups
 // each own one row of the pair — half the hand-offs per row, same data path.
-template <int FOLD, int EPI>
+//
+// GP = group-planar input: the concat buffer is stored as one dense plane [N][H][W][16] per 16-channel group, so a strip
+// row of one group is 4 KB of CONTIGUOUS memory.  A pixel line of the NHWC layout (32-128 useful bytes every 256) costs
+// the L2 one request per pixel and K-chunk whatever its length, which bounded the NHWC form at ~7 cycles per pixel and
+// SM; contiguous 32-byte lines merge into full 128-byte requests (profiles/r01_bulk_probe.log: 4.3-6.3 TB/s for one to
+// five groups).  One group = one K=16 MMA step: stage = [group][row][128 px x 32 B] in SWIZZLE_32B, the A descriptor of
+// tap s starts s pixels (s * 32 B) into the row.
+template <int FOLD, int EPI, bool GP>
 __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_constant__ CUtensorMap tmapA, const SParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int kStage2 = 2 * kStage;
+  const uint32_t kStage2 = GP ? uint32_t(P.stage_bytes) : uint32_t(2 * kStage);
+  constexpr uint32_t kGroupBytes = 8192, kGroupRow = 4096;  // GP: two rows of one 16-channel group / one row
   uint8_t* sA = smem;
   uint8_t* sW = sA + size_t(P.SA) * kStage2 + 1024;
   float* s_pre_s = reinterpret_cast<float*>(sW + P.wbytes);
   float* s_pre_t = s_pre_s + P.nchunks * 64;
   float* s_bias = s_pre_t + P.nchunks * 64;
 
-  __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], raw_full[kMaxSA], acc_done[kMaxR / 2], acc_free[kMaxR / 2], w_full;
+  __shared__ uint64_t a_full[kMaxSA2], a_empty[kMaxSA2], raw_full[kMaxSA2], acc_done[kMaxR / 2], acc_free[kMaxR / 2], w_full;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -712,7 +722,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
   constexpr int kEpiWarps = 8, kWorkWarp0 = kEpiWarp0 + kEpiWarps;
 
   if (tid == 0) {
-    for (int i = 0; i < kMaxSA; ++i) {
+    for (int i = 0; i < kMaxSA2; ++i) {
       ptx::mbar_init(&a_full[i], 8);
       ptx::mbar_init(&a_empty[i], 1);
       ptx::mbar_init(&raw_full[i], 1);
@@ -729,10 +739,18 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
     ptx::tmem_alloc(&tmem_base_s, 512);
     ptx::tmem_relinquish();
   }
+  // GP: BatchNorm scale / shift as bf16 tables (the workers' packed HFMA2 operands), in the space of the fp32 scale table
+  __nv_bfloat16* s_sc = reinterpret_cast<__nv_bfloat16*>(s_pre_s);
+  __nv_bfloat16* s_sh = s_sc + P.nchunks * 64;
   for (int i = tid; i < P.nchunks * 64; i += blockDim.x) {
     const bool ok = i < P.Cin;
-    s_pre_s[i] = ok ? P.pre_s[i] : 0.f;
-    s_pre_t[i] = ok ? P.pre_t[i] : 0.f;
+    if (GP) {
+      s_sc[i] = __float2bfloat16_rn(ok ? P.pre_s[i] : 0.f);
+      s_sh[i] = __float2bfloat16_rn(ok ? P.pre_t[i] : 0.f);
+    } else {
+      s_pre_s[i] = ok ? P.pre_s[i] : 0.f;
+      s_pre_t[i] = ok ? P.pre_t[i] : 0.f;
+    }
   }
   for (int i = tid; i < P.NT; i += blockDim.x) s_bias[i] = P.bias[i];
   ptx::tc_fence_before_sync();
@@ -765,8 +783,16 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
         for (int c = 0; c < P.nchunks; ++c) {
           ptx::mbar_wait(&a_empty[st.i], (st.w & 1) ^ 1);
           if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(&raw_full[st.i], kStage2);
-            ptx::tma_load_4d(sA + size_t(st.i) * kStage2, &tmapA, c * 64, it.w0 - PAD, j, it.n, &raw_full[st.i]);
+            if (GP) {
+              const int ng = min(4, (P.Cin >> 4) - 4 * c);
+              ptx::mbar_arrive_expect_tx(&raw_full[st.i], uint32_t(ng) * kGroupBytes);
+              for (int g = 0; g < ng; ++g)
+                ptx::tma_load_4d(sA + size_t(st.i) * kStage2 + size_t(g) * kGroupBytes, &tmapA, 0, it.w0 - PAD, j,
+                                 it.n + (4 * c + g) * P.N, &raw_full[st.i]);
+            } else {
+              ptx::mbar_arrive_expect_tx(&raw_full[st.i], kStage2);
+              ptx::tma_load_4d(sA + size_t(st.i) * kStage2, &tmapA, c * 64, it.w0 - PAD, j, it.n, &raw_full[st.i]);
+            }
           }
           __syncwarp();
           st.step(P.SA);
@@ -778,6 +804,9 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
     const uint32_t idesc = ptx::umma_idesc_bf16(128, P.NMMA);
     const uint64_t desc_hi = ptx::umma_desc_sw128(0, 1024) & 0xffffffff00000000ull;
     const uint32_t flags = uint32_t(ptx::umma_desc_sw128(0, 1024) & 0xffffffffull);
+    const uint64_t adesc_hi = GP ? (ptx::umma_desc_sw32(0, 256) & 0xffffffff00000000ull) : desc_hi;
+    const uint32_t a_row = GP ? (kGroupRow >> 4) : uint32_t(kStage >> 4);  // descriptor units (16 B) per image row
+    const uint32_t a_tap = GP ? 2u : 8u, a_k = GP ? (kGroupBytes >> 4) : 2u;  // per horizontal tap (one pixel) / per K=16 step
     const uint32_t a_base = flags | ((ptx::smem_u32(sA) & 0x3FFFFu) >> 4);
     const uint32_t b_base = flags | ((ptx::smem_u32(sW) & 0x3FFFFu) >> 4);
     const uint32_t blk16 = uint32_t(P.NMMA) * 8u;
@@ -807,19 +836,19 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
               const uint32_t dc = tmem_base + uint32_t((dr.i + r) * P.SW);  // dr.i is even and R is even: no wrap
-              const uint32_t ar = a0 + uint32_t(r) * (kStage >> 4);
+              const uint32_t ar = a0 + uint32_t(r) * a_row;
               if (RFOLD) {
 #pragma unroll
                 for (int s = 0; s < 3; ++s)
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
                     if (k < ksteps)
-                      ptx::umma_bf16(dc, desc_hi | (ar + uint32_t(8 * s + 2 * k)), desc_hi | (b0 + uint32_t(s) * blk16 + uint32_t(2 * k)), idesc, 1u);
+                      ptx::umma_bf16(dc, adesc_hi | (ar + uint32_t(s) * a_tap + uint32_t(k) * a_k), desc_hi | (b0 + uint32_t(s) * blk16 + uint32_t(2 * k)), idesc, 1u);
               } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   if (k < ksteps)
-                    ptx::umma_bf16(dc, desc_hi | (ar + uint32_t(2 * k)), desc_hi | (b0 + uint32_t(2 * k)), idesc, (c | k) != 0 ? 1u : 0u);
+                    ptx::umma_bf16(dc, adesc_hi | (ar + uint32_t(k) * a_k), desc_hi | (b0 + uint32_t(2 * k)), idesc, (c | k) != 0 ? 1u : 0u);
               }
             }
             ptx::umma_commit(&a_empty[st.i]);
@@ -911,6 +940,53 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
     const int aw = warp - kWorkWarp0;
     const int grp = aw >> 3, t = (aw & 7) * 32 + lane, u = t & 7, qb = t >> 3;
     const uint32_t sA_u = ptx::smem_u32(sA);
+    if (GP) {
+      // thread <-> (pixel p, 16-byte half h) of every group row: SWIZZLE_32B swaps the halves of pixels with bit 2 set
+      const int p = t >> 1, h = t & 1;
+      const uint32_t offp = uint32_t(p) * 32u + (uint32_t((h ^ (p >> 2)) & 1) << 4);
+      const uint32_t sc_u = ptx::smem_u32(s_sc) + uint32_t(h) * 16u, sh_u = ptx::smem_u32(s_sh) + uint32_t(h) * 16u;
+      Ring st;
+      int turn = 0;
+      for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+        const Item it = decode_item(P, item);
+        const int col = it.w0 - PAD + p;
+        const bool ok = col >= 0 && col < P.W;
+        const int npairs = (it.h1 - it.h0 + 2 * PAD + 1) >> 1;
+        for (int pp = 0; pp < npairs; ++pp) {
+          const int j = it.h0 - PAD + 2 * pp;
+          for (int c = 0; c < P.nchunks; ++c, turn ^= 1, st.step(P.SA)) {
+            if (turn != grp) continue;
+            const int ng = min(4, (P.Cin >> 4) - 4 * c);
+            ptx::mbar_wait(&raw_full[st.i], st.w & 1);
+            if (ok) {
+              const uint32_t base = sA_u + uint32_t(st.i) * kStage2 + offp;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (g >= ng) break;
+                uint4 x[2];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) x[r] = ptx::lds128(base + uint32_t(g) * kGroupBytes + uint32_t(r) * kGroupRow);
+                const uint4 csc = ptx::lds128(sc_u + uint32_t(c * 64 + g * 16) * 2u), csh = ptx::lds128(sh_u + uint32_t(c * 64 + g * 16) * 2u);
+                const __nv_bfloat162* gsc = reinterpret_cast<const __nv_bfloat162*>(&csc);
+                const __nv_bfloat162* gsh = reinterpret_cast<const __nv_bfloat162*>(&csh);
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                  __nv_bfloat162* v = reinterpret_cast<__nv_bfloat162*>(&x[r]);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) v[e] = __hfma2_relu(v[e], gsc[e], gsh[e]);
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r)  // rows outside the image keep TMA's zero fill (padding after activation)
+                  if (j + r >= 0 && j + r < P.H) ptx::sts128(base + uint32_t(g) * kGroupBytes + uint32_t(r) * kGroupRow, x[r]);
+              }
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&a_full[st.i]);
+          }
+        }
+      }
+    } else {
     uint32_t off[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) off[i] = ptx::sw128_offset(uint32_t(qb + 32 * i), uint32_t(u));
@@ -968,6 +1044,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
           if (lane == 0) ptx::mbar_arrive(&a_full[st.i]);
         }
       }
+    }
     }
   }
 
@@ -1137,6 +1214,12 @@ void stream_pack_destroy(StreamPack* p) {
 bool conv_stream_supported(const ConvDesc& d, const StreamPack& pk) {
   if (d.in_nchw) return pk.d_wk && d.Cin == 3 && d.W % 4 == 0 && d.relu && !d.pre_scale && !d.out_nchw && d.out_ld % 8 == 0 && (!d.pool || !((d.H | d.W) & 1));
   if (d.Cin % 8 != 0 || d.in_ld % 8 != 0) return false;
+  if (d.in_gstride) {  // group-planar input: dense pre-activation layers of the two-row kernel only
+    if (!d.pre_scale || d.relu || d.pool || d.Cin % 16 != 0 || d.in_ld != 16) return false;
+    if (d.in_gstride != size_t(d.N) * d.H * d.W * 16) return false;  // planes must be contiguous (one tensor map)
+    if (d.ks == 3) return pk.d_wr && !d.out_nchw && d.out_ld % 8 == 0;
+    return pk.d_w && pk.NT > 0 && (d.out_nchw ? d.Cout <= 16 : d.out_ld % 8 == 0);
+  }
   if ((d.relu != 0) != (d.pre_scale == nullptr)) return false;  // ReLU is compiled in per input mode
   if (d.ks == 3 && !d.pre_scale) {  // TMA-fed 3x3: nine-tap fold for 16-wide outputs, else wide form (weights resident)
     if (d.out_nchw || d.out_ld % 8 != 0) return false;
@@ -1187,7 +1270,8 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   // selects the one-row kernel (nine-tap fold) instead.
   static const int rps_env = getenv("CDAN_RPS") ? atoi(getenv("CDAN_RPS")) : 2;
   bool rps2 = false;
-  if (rps_env != 1 && !dual && in_mode == kSPro && !d.pool) {
+  const bool gp = d.in_gstride != 0;
+  if ((rps_env != 1 || gp) && !dual && in_mode == kSPro && !d.pool) {
     const size_t wb = fold == 3 ? (pk.d_wr && !d.out_nchw ? pk.rfold_bytes : 0) : pk.pass_bytes;
     const int tail2 = 2 * pk.nchunks * 64 * 4 + 128 * 4 + 256;
     rps2 = wb > 0 && (kSmemLimit - 1024 - int(wb) - tail2) / (2 * kStage) >= 4;
@@ -1215,8 +1299,10 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   P.out_ld = d.out_ld; P.out_nchw = d.out_nchw;
   P.wbytes = uint32_t(kfold ? size_t(192) * 128 : (wide ? pk.wide_bytes : (rfold ? pk.rfold_bytes : pk.pass_bytes)));
   const int tail = 2 * P.nchunks * 64 * 4 + std::max(P.NT, 64) * 4 + 256 + (kfold ? kRawStages * kRawFloats * 4 + 128 : 0);
-  const int stage_bytes = rps2 ? 2 * kStage : kStage;
-  P.SA = std::min(kMaxSA, ((dual ? kSmemLimit2 : kSmemLimit) - 1024 - int(P.wbytes) - tail) / stage_bytes);
+  if (gp && !rps2) return fail("conv_stream: group-planar input needs the two-row kernel (weights too large)");
+  P.stage_bytes = gp ? std::min(4, d.Cin / 16) * 8192 : 0;
+  const int stage_bytes = gp ? P.stage_bytes : (rps2 ? 2 * kStage : kStage);
+  P.SA = std::min(gp ? kMaxSA2 : kMaxSA, ((dual ? kSmemLimit2 : kSmemLimit) - 1024 - int(P.wbytes) - tail) / stage_bytes);
   // The two worker groups take alternate stages: with an even stage count every ring slot always belongs to the same
   // group.  (With an odd count a group could test a slot's mbarrier parity a full phase ahead of the last phase it
   // observed there — parity waits then return a false positive and the pipeline desynchronises.)
@@ -1232,15 +1318,16 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
     PFN_encodeTiled enc = stream_get_encode();
     if (!enc) return fail("conv_stream: cuTensorMapEncodeTiled is not available from the driver");
     if (reinterpret_cast<uintptr_t>(d.in) % 16 != 0) return fail("conv_stream: input pointer must be 16-byte aligned");
-    cuuint64_t gdim[4] = {cuuint64_t(d.Cin), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.N)};
+    // group-planar: the planes of all groups form one [N * groups][H][W][16] tensor, image n of group g = index n + g*N
+    cuuint64_t gdim[4] = {cuuint64_t(gp ? 16 : d.Cin), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(gp ? d.N * (d.Cin / 16) : d.N)};
     cuuint64_t gstr[3] = {cuuint64_t(d.in_ld) * 2, cuuint64_t(d.W) * d.in_ld * 2, cuuint64_t(d.H) * d.W * d.in_ld * 2};
-    cuuint32_t box[4] = {64, cuuint32_t(shift ? 32 : 128), cuuint32_t(rps2 ? 2 : 1), 1};
+    cuuint32_t box[4] = {cuuint32_t(gp ? 16 : 64), cuuint32_t(shift ? 32 : 128), cuuint32_t(rps2 ? 2 : 1), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.in), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, gp ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                      // 128-byte L2 promotion only when every K-chunk is a full 128-byte line; otherwise 64 bytes (ncu: with
                      // promotion NONE a 32-byte line still pulled 128 bytes from DRAM, with 64B it pulls 64)
-                     (d.Cin % 64 == 0 && !getenv("CDAN_PROMO64")) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
+                     (gp || d.Cin % 64 == 0) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("conv_stream: cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
   }
@@ -1287,8 +1374,11 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
     };
     int rc;
     if (rps2) {
-      if (fold == 3) rc = launch(conv_stream2_kernel<4, kSStore>);
-      else rc = d.out_nchw ? launch(conv_stream2_kernel<1, kSNchwOut>) : launch(conv_stream2_kernel<1, kSStore>);
+      if (gp) {
+        if (fold == 3) rc = launch(conv_stream2_kernel<4, kSStore, true>);
+        else rc = d.out_nchw ? launch(conv_stream2_kernel<1, kSNchwOut, true>) : launch(conv_stream2_kernel<1, kSStore, true>);
+      } else if (fold == 3) rc = launch(conv_stream2_kernel<4, kSStore, false>);
+      else rc = d.out_nchw ? launch(conv_stream2_kernel<1, kSNchwOut, false>) : launch(conv_stream2_kernel<1, kSStore, false>);
     } else if (kfold) rc = d.pool ? launch(conv_stream_kernel<kSNchw, 3, kSPool>) : launch(conv_stream_kernel<kSNchw, 3, kSStore>);
     else if (fold == 3) {
       if (d.out_nchw) rc = in_mode == kSPro ? launch(conv_stream_kernel<kSPro, 3, kSNchwOut>) : launch(conv_stream_kernel<kSTma, 3, kSNchwOut>);

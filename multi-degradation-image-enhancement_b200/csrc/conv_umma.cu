@@ -565,6 +565,7 @@ int conv_umma_launch(const ConvDesc& d, const UmmaPack& pk, cudaStream_t stream)
   if (pk.Cin != d.Cin || pk.Cout != d.Cout || pk.ks != d.ks) return fail("conv_umma: weight pack does not match");
   static const bool use_stream = !(getenv("CDAN_CONV_STREAM") && atoi(getenv("CDAN_CONV_STREAM")) == 0);
   if (use_stream && pk.stream && conv_stream_supported(d, *pk.stream)) return conv_stream_launch(d, *pk.stream, stream);
+  if (d.in_gstride) return fail("conv_umma: group-planar input is only implemented by the streaming kernel");
   const int in_mode = d.in_nchw ? kInNchw3 : (d.pre_scale ? kInPro : kInTma);
   TileCfg tc;
   if (!choose_tiles(d, pk.NT, in_mode, &tc)) return fail("conv_umma: no tile configuration fits shared memory");

@@ -211,6 +211,12 @@ void free_weights(cdan_plan* p) {
 // Channel stride of the final dense block's concat buffer: 80 channels are used, the pixel is padded to 128 channels
 // (256 B) so that every channel-prefix read starts and ends on a 64-byte DRAM atom (measured: 160-byte pixels make the
 // 128-byte prefix of layer 3 fetch the whole buffer and cost ~6 % of the step; 192-byte pixels are worse still).
+// CDAN_FD_PLANAR=0 keeps the final dense block NHWC (A/B switch); the planar form needs the streaming kernels.
+bool fd_planar_enabled() {
+  static const bool v = !(getenv("CDAN_FD_PLANAR") && atoi(getenv("CDAN_FD_PLANAR")) == 0) &&
+                        !(getenv("CDAN_CONV_STREAM") && atoi(getenv("CDAN_CONV_STREAM")) == 0);
+  return v;
+}
 int fd_ld() {
   static const int v = getenv("CDAN_FD_LD") ? atoi(getenv("CDAN_FD_LD")) : 128;
   return v;
@@ -299,12 +305,13 @@ struct SpanGuard {  // records a pair of events around the launches issued in it
 int conv_dispatch(cdan_plan* p, const ConvLayer& L, const ConvDesc& d, cudaStream_t s);  // below
 
 int run_conv(cdan_plan* p, ConvId id, int N, int H, int W, const void* in, int in_ld, void* out, int out_ld,
-             int pool, cudaStream_t s, const float* in_nchw = nullptr, float* out_nchw = nullptr, int sigmoid = 0) {
+             int pool, cudaStream_t s, const float* in_nchw = nullptr, float* out_nchw = nullptr, int sigmoid = 0,
+             size_t in_gstride = 0) {
   const ConvLayer& L = p->conv[id];
   ConvDesc d;
   d.N = N; d.H = H; d.W = W;
   d.Cin = L.Cin; d.Cout = L.Cout; d.ks = L.ks;
-  d.in = in; d.in_ld = in_ld; d.in_nchw = in_nchw;
+  d.in = in; d.in_ld = in_ld; d.in_nchw = in_nchw; d.in_gstride = in_gstride;
   d.pre_scale = L.d_pre_s; d.pre_shift = L.d_pre_t;
   d.w = L.d_w; d.CoutP = L.CoutP; d.bias = L.d_bias;
   d.relu = L.relu; d.pool = pool;
@@ -336,6 +343,15 @@ int run_dense(cdan_plan* p, ConvId first, int N, int h, int w, void* D, int ld, 
   (void)Cout;
   return run_conv(p, ConvId(first + 4), N, h, w, D, ld, DN, DN ? p->conv[first + 4].Cout : 0, 0, s, nullptr, out_nchw,
                   out_nchw ? 1 : 0);
+}
+
+// final dense block in the GROUP-PLANAR layout (bf16 tensor-core plans): plane g of D holds channels [16g, 16g+16) as a
+// dense [N][h][w][16] tensor; layer l reads planes 0..l and writes plane l+1, the transition reads all five.
+int run_dense_planar(cdan_plan* p, ConvId first, int N, int h, int w, void* D, cudaStream_t s, float* out_nchw) {
+  const size_t gs = size_t(N) * h * w * 16;
+  for (int l = 0; l < 4; ++l)
+    CDAN_TRY(run_conv(p, ConvId(first + l), N, h, w, D, 16, at(D, gs * (1 + l), p->dt), 16, 0, s, nullptr, nullptr, 0, gs));
+  return run_conv(p, ConvId(first + 4), N, h, w, D, 16, nullptr, 0, 0, s, nullptr, out_nchw, 1, gs);
 }
 
 int run_cbam(cdan_plan* p, int slot, const void* x, const void* mul, void* out, int N, int h, int w, bool pooled,
@@ -397,10 +413,14 @@ int forward_impl(cdan_plan* p, cudaStream_t s, const float* x, float* y, int N, 
   CDAN_TRY(run_up_add(p, 3, b.T3, 64, b.D1, 128, b.U3, N, H2, W2, 1, s));
   CDAN_TRY(run_cbam(p, 3, b.U3, b.DN1, b.C3, N, H2, W2, true, s));
   CDAN_TRY(run_conv(p, DEC4, N, H2, W2, b.C3, 64, b.T4, 8, 0, s));
-  { SpanGuard span(p, s, "glue|up_add_input"); CDAN_TRY(up_add_input_launch(dt, b.T4, 8, x, b.FD, fd_ld(), 16, N, H, W, s)); }
+  // The final dense block's concat buffer is group-planar on the tensor-core path, NHWC otherwise.
+  const bool fd_planar = dt == kBF16 && p->conv_impl == 0 && fd_planar_enabled();
+  const int fdl = fd_planar ? 16 : fd_ld();
+  { SpanGuard span(p, s, "glue|up_add_input"); CDAN_TRY(up_add_input_launch(dt, b.T4, 8, x, b.FD, fdl, 16, N, H, W, s)); }
   p->launches += 1;
   // final DenseBlock(3,3,16,4) + sigmoid, written straight to the caller's fp32 NCHW output
-  CDAN_TRY(run_dense(p, FDL0, N, H, W, b.FD, fd_ld(), 16, nullptr, 3, s, y));
+  if (fd_planar) CDAN_TRY(run_dense_planar(p, FDL0, N, H, W, b.FD, s, y));
+  else CDAN_TRY(run_dense(p, FDL0, N, H, W, b.FD, fd_ld(), 16, nullptr, 3, s, y));
 
   auto& st = p->stages;
   st.clear();
@@ -419,7 +439,7 @@ int forward_impl(cdan_plan* p, cudaStream_t s, const float* x, float* y, int N, 
   st["dec.bn3"] = {b.T3, 64, 64, H4, W4};
   st["dec.gated3"] = {b.C3, 64, 64, H2, W2};
   st["dec.bn4"] = {b.T4, 3, 8, H2, W2};
-  st["dec.final_in"] = {b.FD, 3, fd_ld(), H, W};
+  st["dec.final_in"] = {b.FD, 3, fdl, H, W};
   return 0;
 }
 

@@ -188,6 +188,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
+// Same for a 32-byte-swizzled K-major operand (one K=16 step per row: rows 32 B apart, groups of eight rows
+// `sbo_bytes` apart, 256 for a dense tile; the 16-byte halves of a row are swapped when address bit 7 is set).
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
+  d |= uint64_t(1) << 16;
+  d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(6) << 61;  // SWIZZLE_32B
+  return d;
+}
+
 // TMEM -> registers: this warp's 32 lanes x 16 consecutive fp32 columns (thread t <- lane 32*(warp%4)+t).
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
