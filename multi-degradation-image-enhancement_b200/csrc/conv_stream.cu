@@ -144,6 +144,11 @@ struct SlotPhases {
     par ^= 1u << s;
   }
   __device__ __forceinline__ void skip(int s) { par ^= 1u << s; }  // a use observed by someone else
+  // producer side, a use claimed by ANOTHER producer thread: same bookkeeping as claim() without the wait
+  __device__ __forceinline__ void note(int s) {
+    if ((used >> s) & 1u) par ^= 1u << s;
+    used |= 1u << s;
+  }
   // producer side: before the first write of a new use, wait until the previous use (if any) was drained
   __device__ __forceinline__ void claim(uint64_t* free_bars, int s) {
     if ((used >> s) & 1u) wait(free_bars, s);
@@ -713,7 +718,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
   float* s_pre_t = s_pre_s + P.nchunks * 64;
   float* s_bias = s_pre_t + P.nchunks * 64;
 
-  __shared__ uint64_t a_full[kMaxSA2], a_empty[kMaxSA2], raw_full[kMaxSA2], acc_done[kMaxR / 2], acc_free[kMaxR / 2], w_full;
+  __shared__ uint64_t a_full[kMaxSA2], a_empty[kMaxSA2], raw_full[kMaxSA2], acc_done[kMaxR / 2], acc_free[kMaxR / 2], w_full, mma_turn[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -732,6 +737,8 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
       ptx::mbar_init(&acc_free[i], 8);
     }
     ptx::mbar_init(&w_full, 1);
+    ptx::mbar_init(&mma_turn[0], 1);
+    ptx::mbar_init(&mma_turn[1], 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tmapA);
   }
@@ -793,14 +800,21 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
               ptx::mbar_arrive_expect_tx(&raw_full[st.i], kStage2);
               ptx::tma_load_4d(sA + size_t(st.i) * kStage2, &tmapA, c * 64, it.w0 - PAD, j, it.n, &raw_full[st.i]);
             }
+            STRACE(0, st.w * P.SA + st.i);
           }
           __syncwarp();
           st.step(P.SA);
         }
       }
     }
-  } else if (warp == 1) {
-    // ============================================================ MMA issuer
+  } else if (warp == 1 || warp == 3) {
+    // ============================================================ MMA issuers (two warps, alternate row pairs)
+    // One issuing thread spends ~1100 cycles per row pair on hand-offs (two mbarrier waits, the tcgen05 fence, three
+    // commits) during which the tensor pipe drains: it queues only a few MMAs, so issue time and hand-off time ADD
+    // (timeline traces in profiles/r01_trace_stream2.md).  Two issuers take alternate row pairs; the order of the
+    // accumulations is kept by a token: an issuer starts its pair only after the other's MMAs have COMPLETED
+    // (tcgen05.commit on mma_turn), so its hand-offs overlap the other's MMAs and results stay bitwise deterministic.
+    const int mw = warp >> 1;
     const uint32_t idesc = ptx::umma_idesc_bf16(128, P.NMMA);
     const uint64_t desc_hi = ptx::umma_desc_sw128(0, 1024) & 0xffffffff00000000ull;
     const uint32_t flags = uint32_t(ptx::umma_desc_sw128(0, 1024) & 0xffffffffull);
@@ -812,58 +826,104 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
     const uint32_t blk16 = uint32_t(P.NMMA) * 8u;
     const int klast = min(4, (P.Cin - (P.nchunks - 1) * 64 + 15) >> 4);
     Ring st, dr;    // stage; ring slot of the first accumulator row of the current pair (tied to the absolute image row)
-    SlotPhases fp;  // acc_free phases, one bit per slot pair
+    SlotPhases fp;  // acc_free phases, one bit per slot pair (both issuers track every slot)
+    uint32_t gp = 0, tok = 0;  // global pair sequence number; tokens consumed by this issuer
+    uint32_t prev_mask = 0;    // accumulator slot pairs claimed for pair gp - 1 (by the other issuer)
     ptx::mbar_wait(&w_full, 0);
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const Item it = decode_item(P, item);
       const int npairs = (it.h1 - it.h0 + 2 * PAD + 1) >> 1;
       dr.i = it.h0 % P.R;  // even: segments start at even rows, R is even
-      if (PAD) fp.claim(acc_free, dr.i >> 1);  // the first input pair also opens the segment's first accumulator pair
-      for (int pp = 0; pp < npairs; ++pp) {
-        {
-          int newest = dr.i + 2 * PAD;  // newest accumulator pair this input pair touches
-          if (newest >= P.R) newest -= P.R;
-          fp.claim(acc_free, newest >> 1);
+      for (int pp = 0; pp < npairs; ++pp, ++gp) {
+        const bool mine = (gp & 1u) == uint32_t(mw);
+        int newest = dr.i + 2 * PAD;  // newest accumulator pair this input pair touches
+        if (newest >= P.R) newest -= P.R;
+        // slot pairs this input pair opens: the newest one, and at a segment start (3x3) also the segment's first
+        const int s1 = newest >> 1, s0 = (PAD && pp == 0) ? (dr.i >> 1) : s1;
+        const uint32_t cur_mask = (1u << s1) | (1u << s0);
+        if (!mine) {
+          fp.note(s1);
+          if (s0 != s1) fp.note(s0);
+          prev_mask = cur_mask;
+          for (int c = 0; c < P.nchunks; ++c) st.step(P.SA);
+          dr.add(2, P.R);
+          continue;
         }
-        ptx::tc_fence_after_sync();
+        // A slot may be claimed ahead of the token only if its previous use is older than the other issuer's current
+        // pair: otherwise that use's own claim may still be pending and a parity wait one phase ahead returns a false
+        // positive (ring positions jump at segment starts, so consecutive pairs can meet in one slot).
+        const uint32_t deferred = cur_mask & prev_mask;
+        if (!((deferred >> s1) & 1u)) fp.claim(acc_free, s1);
+        if (s0 != s1 && !((deferred >> s0) & 1u)) fp.claim(acc_free, s0);
+        prev_mask = cur_mask;
+        if (mw == 0 && lane == 0) STRACE(7, st.w * P.SA + st.i);
         uint32_t b0 = b_base;
         for (int c = 0; c < P.nchunks; ++c) {
           const int ksteps = c == P.nchunks - 1 ? klast : 4;
-          ptx::mbar_wait(&a_full[st.i], st.w & 1);
+          // The first stage of a pair may be waited for ahead of the token only if its previous use lies before the
+          // other issuer's current pair (SA > nchunks): otherwise that use may not even be filled yet and a parity
+          // wait one phase ahead returns a false positive.
+          const bool late = c == 0 && gp > 0 && P.SA <= P.nchunks;
+          if (!late) ptx::mbar_wait(&a_full[st.i], st.w & 1);
+          if (c == 0 && gp > 0) {  // the other issuer's pair has completed
+            ptx::mbar_wait(&mma_turn[mw], tok & 1u);
+            ++tok;
+            if (deferred) {
+              if ((deferred >> s1) & 1u) fp.claim(acc_free, s1);
+              if (s0 != s1 && ((deferred >> s0) & 1u)) fp.claim(acc_free, s0);
+            }
+          }
+          if (late) ptx::mbar_wait(&a_full[st.i], st.w & 1);
+          if (mw == 0 && lane == 0) STRACE(3, st.w * P.SA + st.i);
           ptx::tc_fence_after_sync();
           const uint32_t a0 = a_base + uint32_t(st.i) * (kStage2 >> 4);
           if (ptx::elect_one()) {
+            // One dynamic loop over the K=16 steps of the chunk, the (row, tap) MMAs of a step unrolled with immediate
+            // descriptor offsets (a fully predicated 24-MMA unroll cost ~250 instructions per stage).
+            const uint32_t dc0 = tmem_base + uint32_t(dr.i * P.SW);  // dr.i is even and R is even: no wrap inside a pair
+            uint32_t ak = a0, bk = b0;
+            if (!(P.ablate & 4)) {
+              for (int k = 0; k < ksteps; ++k, ak += a_k, bk += 2u) {
+                if (RFOLD) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              const uint32_t dc = tmem_base + uint32_t((dr.i + r) * P.SW);  // dr.i is even and R is even: no wrap
-              const uint32_t ar = a0 + uint32_t(r) * a_row;
-              if (RFOLD) {
+                  for (int r = 0; r < 2; ++r)
 #pragma unroll
-                for (int s = 0; s < 3; ++s)
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    if (k < ksteps)
-                      ptx::umma_bf16(dc, adesc_hi | (ar + uint32_t(s) * a_tap + uint32_t(k) * a_k), desc_hi | (b0 + uint32_t(s) * blk16 + uint32_t(2 * k)), idesc, 1u);
-              } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (k < ksteps)
-                    ptx::umma_bf16(dc, adesc_hi | (ar + uint32_t(k) * a_k), desc_hi | (b0 + uint32_t(2 * k)), idesc, (c | k) != 0 ? 1u : 0u);
+                    for (int s = 0; s < 3; ++s)
+                      ptx::umma_bf16(dc0 + uint32_t(r * 16), adesc_hi | (ak + uint32_t(r) * a_row + uint32_t(s) * a_tap),
+                                     desc_hi | (bk + uint32_t(s * 48 * 8)), idesc, 1u);
+                } else {
+                  const uint32_t acc = (c | k) != 0 ? 1u : 0u;
+                  ptx::umma_bf16(dc0, adesc_hi | ak, desc_hi | bk, idesc, acc);
+                  ptx::umma_bf16(dc0 + uint32_t(P.SW), adesc_hi | (ak + a_row), desc_hi | bk, idesc, acc);
+                }
               }
             }
             ptx::umma_commit(&a_empty[st.i]);
+            if (c == P.nchunks - 1) {
+              ptx::umma_commit(&acc_done[dr.i >> 1]);
+              ptx::umma_commit(&mma_turn[mw ^ 1]);
+            }
+            if (mw == 0) STRACE(4, st.w * P.SA + st.i);
           }
           __syncwarp();
           st.step(P.SA);
           b0 += RFOLD ? 3u * blk16 : blk16;
         }
-        if (ptx::elect_one()) ptx::umma_commit(&acc_done[dr.i >> 1]);
-        __syncwarp();
         dr.add(2, P.R);
       }
       if (PAD) {  // the trailing accumulator-row pair of the segment receives no further input
-        if (ptx::elect_one()) ptx::umma_commit(&acc_done[dr.i >> 1]);
-        __syncwarp();
+        if ((gp & 1u) == uint32_t(mw)) {
+          ptx::mbar_wait(&mma_turn[mw], tok & 1u);  // gp > 0 here: every segment has at least one input pair
+          ++tok;
+          ptx::tc_fence_after_sync();
+          if (ptx::elect_one()) {
+            ptx::umma_commit(&acc_done[dr.i >> 1]);
+            ptx::umma_commit(&mma_turn[mw ^ 1]);
+          }
+          __syncwarp();
+        }
+        prev_mask = 0;
+        ++gp;
         dr.add(2, P.R);
       }
     }
@@ -889,11 +949,12 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
       for (int pp = 0; pp < n_acc_pairs; ++pp) {
         const int pslot = pr.i >> 1, slot = pr.i + eg;
         dp.wait(acc_done, pslot);
+        if (eg == 0 && q == 0 && lane == 0 && item == int(blockIdx.x)) STRACE(5, pp);
         ptx::tc_fence_after_sync();
         const bool row_ok = i >= it.h0 && i < it.h1;
         const bool shadow = PAD && slot < 2;
         const uint32_t tm = lb + uint32_t(slot * P.SW), ts = lb + uint32_t((P.R + slot) * P.SW);
-        for (int c0 = 0; c0 < P.NT; c0 += 8) {
+        for (int c0 = 0; c0 < ((P.ablate & 8) ? 0 : P.NT); c0 += 8) {
           uint32_t v[8];
           if (row_ok) {
             ptx::tmem_ld8(tm + c0, v);
@@ -921,7 +982,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
 #pragma unroll
               for (int e = 0; e < 8; ++e)
                 if (c0 + e < P.Cout) o_f[size_t(c0 + e) * plane] = P.sigmoid ? 1.0f / (1.0f + __expf(-f[e])) : f[e];
-            } else if (c0 < P.Cout) {  // channel slices are padded to multiples of 8
+            } else if (c0 < P.Cout && !(P.ablate & 1)) {  // channel slices are padded to multiples of 8
               *reinterpret_cast<uint4*>(o_b + c0) = make_uint4(bf2(f[0], f[1]), bf2(f[2], f[3]), bf2(f[4], f[5]), bf2(f[6], f[7]));
             }
           }
@@ -930,6 +991,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&acc_free[pslot]);
+        if (eg == 0 && q == 0 && lane == 0 && item == int(blockIdx.x)) STRACE(6, pp);
         pr.add(2, P.R);
         i += 2;
         if (EPI == kSNchwOut) o_f += 2 * row_elems; else o_b += 2 * row_elems;
@@ -958,7 +1020,8 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
             if (turn != grp) continue;
             const int ng = min(4, (P.Cin >> 4) - 4 * c);
             ptx::mbar_wait(&raw_full[st.i], st.w & 1);
-            if (ok) {
+            if ((aw & 7) == 0 && lane == 0) STRACE(1, st.w * P.SA + st.i);
+            if (ok && !(P.ablate & 2)) {
               const uint32_t base = sA_u + uint32_t(st.i) * kStage2 + offp;
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -983,6 +1046,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&a_full[st.i]);
+            if ((aw & 7) == 0 && lane == 0) STRACE(2, st.w * P.SA + st.i);
           }
         }
       }
@@ -1405,7 +1469,7 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
     const char* names[8] = {"tma_issue", "act_start", "act_done", "mma_start", "mma_issued", "epi_start", "epi_done", "mma_rowgo"};
     for (int r = 0; r < 8; ++r) {
       fprintf(stderr, "%-10s", names[r]);
-      for (int i = 0; i < 48; ++i) fprintf(stderr, " %6lld", t[r * kTraceN + i] ? (long long)(t[r * kTraceN + i] - t0) : -1ll);
+      for (int i = 0; i < 96; ++i) fprintf(stderr, " %6lld", t[r * kTraceN + i] ? (long long)(t[r * kTraceN + i] - t0) : -1ll);
       fprintf(stderr, "\n");
     }
   }
