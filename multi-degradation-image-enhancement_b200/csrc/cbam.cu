@@ -149,6 +149,63 @@ __global__ void __launch_bounds__(256) compress_kernel(const T* __restrict__ x, 
   }
 }
 
+// Same reduction (identical summation order) for C <= 512, restructured for bandwidth: one image per blockIdx.y so the
+// channel gate of a lane stays in registers, and U pixels per lane and iteration so U x VPL independent 16-byte loads
+// are in flight per thread (the one-load-per-iteration form above ran at 2.3 TB/s).
+template <typename T, int VPL, int U>
+__global__ void __launch_bounds__(256) compress2_kernel(const T* __restrict__ x, int ld, int C, int HW,
+                                                         const float* __restrict__ gate, float* __restrict__ comp) {
+  const int vecs = C >> 3;
+  const int lpp = vecs < 32 ? vecs : 32;  // lanes per pixel
+  const int ppw = 32 / lpp;               // pixels per warp and step
+  const int lane = threadIdx.x % 32, sub = lane % lpp, wp = lane / lpp;
+  const int n = blockIdx.y;
+  float gg[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float* g = gate + size_t(n) * C + (sub + i * lpp) * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(g), g1 = *reinterpret_cast<const float4*>(g + 4);
+    gg[i][0] = g0.x; gg[i][1] = g0.y; gg[i][2] = g0.z; gg[i][3] = g0.w;
+    gg[i][4] = g1.x; gg[i][5] = g1.y; gg[i][6] = g1.z; gg[i][7] = g1.w;
+  }
+  const T* xi = x + size_t(n) * HW * ld;
+  float2* ci = reinterpret_cast<float2*>(comp) + size_t(n) * HW;
+  const int wi = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, nw = gridDim.x * (blockDim.x / 32);
+  const float inv_c = 1.0f / float(C);
+  for (int p0 = wi * ppw * U; p0 < HW; p0 += nw * ppw * U) {
+    F8 a[U][VPL];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pix = p0 + u * ppw + wp;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        if (pix < HW) a[u][i] = load8<T>(xi + size_t(pix) * ld + (sub + i * lpp) * 8);
+        else
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[u][i].v[j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pix = p0 + u * ppw + wp;
+      float mx = -INFINITY, sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = a[u][i].v[j] * gg[i][j];
+          mx = fmaxf(mx, t);
+          sum += t;
+        }
+      for (int o = lpp >> 1; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      }
+      if (sub == 0 && pix < HW) ci[pix] = make_float2(mx, sum * inv_c);
+    }
+  }
+}
+
 // SpatialGate (models/cbam.py:72-82): 7x7 conv over the 2-channel map, zero pad 3, no bias, BN(1), sigmoid.
 // One 16x64 tile per block: the tile + 3-pixel halo of comp is staged in shared memory once (zeros outside the image),
 // then every thread evaluates four pixels from shared memory (98 FMAs each).
@@ -236,7 +293,14 @@ int cbam_typed(const void* x, int x_ld, const void* mul, int mul_ld, void* out, 
   CDAN_CUDA_OK(cudaGetLastError());
   const size_t npix = size_t(N) * HW;
   const int lpp = vecs < 32 ? vecs : 32;
-  compress_kernel<T><<<grid_for(npix * lpp), 256, 0, s>>>((const T*)x, x_ld, C, HW, npix, sc.gate, sc.comp);
+  if (C <= 512) {  // lanes cover the channels of a pixel in at most two 16-byte vectors each
+    constexpr int U = 4;
+    const int ppw = 32 / lpp, bx = std::max(1, std::min(ceil_div(HW, 8 * ppw * U), ceil_div(148 * 8, N)));
+    if (vecs <= 32) compress2_kernel<T, 1, U><<<dim3(bx, N), 256, 0, s>>>((const T*)x, x_ld, C, HW, sc.gate, sc.comp);
+    else compress2_kernel<T, 2, U><<<dim3(bx, N), 256, 0, s>>>((const T*)x, x_ld, C, HW, sc.gate, sc.comp);
+  } else {
+    compress_kernel<T><<<grid_for(npix * lpp), 256, 0, s>>>((const T*)x, x_ld, C, HW, npix, sc.gate, sc.comp);
+  }
   CDAN_CUDA_OK(cudaGetLastError());
   spatial_gate_kernel<<<dim3(ceil_div(W, kSgTW), ceil_div(H, kSgTH), N), 256, 0, s>>>(sc.comp, wt.w7, wt.bn_a, wt.bn_b, sc.sgate, H, W);
   CDAN_CUDA_OK(cudaGetLastError());
