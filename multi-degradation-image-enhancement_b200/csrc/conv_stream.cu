@@ -185,6 +185,9 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
   constexpr uint32_t kTmemCols = IN == kSPro2 ? 256 : 512;
   constexpr bool WIDE = FOLD == 3 && IN == kSTma;
   constexpr bool RELU = !is_pro(IN);  // dense-block layers have no output ReLU; ConvBlock / decoder convs always do
+  // Wide pooled layers (conv2: N = 128, four ring slots) leave the MMA warp one spare accumulator row, so MMA and
+  // epilogue run back to back; both epilogue groups then drain EVERY row pair, half of the channels each.
+  constexpr bool kSplitPool = WIDE && EPI == kSPool && kEG == 2;
 
   if (tid == 0) {
     for (int i = 0; i < kMaxSA; ++i) {
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
     }
     for (int i = 0; i < P.R; ++i) {
       ptx::mbar_init(&acc_done[i], 1);
-      ptx::mbar_init(&acc_free[i], 4);
+      ptx::mbar_init(&acc_free[i], kSplitPool ? 8 : 4);
     }
     ptx::mbar_init(&w_full, 1);
     ptx::fence_mbar_init();
@@ -505,7 +508,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
         int i = it.h0 - 2 * PAD;
         for (int ii = 0; ii < n_acc; ii += 2, ++pairs_seen, sr.add(2, P.R), i += 2) {
           const int sl0 = sr.i, sl1 = sr.i + 1;  // h0 and R are even, so a pair never straddles the ring end
-          if (kEG == 2 && (pairs_seen & 1) != eg) {
+          if (!kSplitPool && kEG == 2 && (pairs_seen & 1) != eg) {
             dp.skip(sl0);
             dp.skip(sl1);
             continue;
@@ -519,7 +522,8 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
           const uint32_t t0 = lb + uint32_t(sl0 * P.NT), t1 = lb + uint32_t(sl1 * P.NT);
           const uint32_t ts0 = lb + uint32_t((P.R + sl0) * P.NT), ts1 = lb + uint32_t((P.R + sl1) * P.NT);
           bf16* o_row = P.out + ((size_t(it.n) * (P.H >> 1) + (i >> 1)) * (P.W >> 1) + (col >> 1)) * P.out_ld;
-          for (int c0 = 0; c0 < P.NT; c0 += 16) {
+          const int cbeg = kSplitPool ? eg * (P.NT >> 1) : 0, cend = kSplitPool ? cbeg + (P.NT >> 1) : P.NT;
+          for (int c0 = cbeg; c0 < cend; c0 += 16) {
             // 16 channels of both rows per TMEM round trip (pooling kernels run with <= 512 threads, i.e. 128 registers)
             uint32_t v0[16], v1[16];
             if (row_ok) {

@@ -588,9 +588,28 @@ int cdan_forward_host(cdan_plan* p, const float* x_host, float* y_host, int N, i
     p->host_stage_bytes = 4 * slot_floats * sizeof(float);
   }
   CDAN_TRY(ensure_workspace(p, cb, H, W));
-  int k = 0;
-  for (int n0 = 0; n0 < N; n0 += cb, ++k) {
-    const int nb = std::min(cb, N - n0), slot = k & 1;
+  // Chunk schedule: full chunks of `cb` images in the middle, a short ramp (cb/4, cb/2) at both ends so that the first
+  // forward starts after a quarter-chunk copy and only a quarter-chunk D2H copy trails the last forward.  Results do not
+  // depend on the schedule (the forward is batch-independent, bitwise).
+  std::vector<int> sched;
+  {
+    std::vector<int> ramp;
+    for (int c = std::max(1, cb / 4); c < cb; c *= 2) ramp.push_back(c);
+    int ramp_sum = 0;
+    for (int c : ramp) ramp_sum += c;
+    if (N >= 2 * ramp_sum + cb) {
+      sched = ramp;
+      int rest = N - 2 * ramp_sum;
+      for (; rest >= cb; rest -= cb) sched.push_back(cb);
+      if (rest > 0) sched.push_back(rest);
+      sched.insert(sched.end(), ramp.rbegin(), ramp.rend());
+    } else {
+      for (int rest = N; rest > 0; rest -= cb) sched.push_back(std::min(cb, rest));
+    }
+  }
+  int k = 0, n0 = 0;
+  for (size_t ci = 0; ci < sched.size(); n0 += sched[ci], ++ci, ++k) {
+    const int nb = sched[ci], slot = k & 1;
     float* xs = p->host_stage + size_t(slot) * 2 * slot_floats;
     float* ys = xs + slot_floats;
     const size_t bytes = size_t(nb) * img_floats * sizeof(float);
