@@ -77,6 +77,7 @@ struct SParams {
   int R;         // ring slots (excluding the two shadow slots)
   int TW, strips, SEG, segs, nitems;
   int nchunks, nS, SA;
+  int ni;           // two-row kernel: number of MMA issuer warps (2 or 3)
   int stage_bytes;  // group-planar input only: bytes per two-row stage (8 KB per 16-channel group)
   int relu, sigmoid, Cout;
   uint32_t wbytes;
@@ -722,7 +723,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
   float* s_pre_t = s_pre_s + P.nchunks * 64;
   float* s_bias = s_pre_t + P.nchunks * 64;
 
-  __shared__ uint64_t a_full[kMaxSA2], a_empty[kMaxSA2], raw_full[kMaxSA2], acc_done[kMaxR / 2], acc_free[kMaxR / 2], w_full, mma_turn[2];
+  __shared__ uint64_t a_full[kMaxSA2], a_empty[kMaxSA2], raw_full[kMaxSA2], acc_done[kMaxR / 2], acc_free[kMaxR / 2], w_full, mma_turn[3];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -743,6 +744,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
     ptx::mbar_init(&w_full, 1);
     ptx::mbar_init(&mma_turn[0], 1);
     ptx::mbar_init(&mma_turn[1], 1);
+    ptx::mbar_init(&mma_turn[2], 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tmapA);
   }
@@ -811,14 +813,17 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
         }
       }
     }
-  } else if (warp == 1 || warp == 3) {
-    // ============================================================ MMA issuers (two warps, alternate row pairs)
+  } else if (warp >= 1 && warp <= 3 && (warp != 2 || P.ni > 2)) {
+    // ============================================================ MMA issuers (P.ni = 2 or 3 warps, row pairs round-robin)
     // One issuing thread spends ~1100 cycles per row pair on hand-offs (two mbarrier waits, the tcgen05 fence, three
     // commits) during which the tensor pipe drains: it queues only a few MMAs, so issue time and hand-off time ADD
     // (timeline traces in profiles/r01_trace_stream2.md).  Two issuers take alternate row pairs; the order of the
     // accumulations is kept by a token: an issuer starts its pair only after the other's MMAs have COMPLETED
     // (tcgen05.commit on mma_turn), so its hand-offs overlap the other's MMAs and results stay bitwise deterministic.
-    const int mw = warp >> 1;
+    // With three issuers (warp 2 joins after allocating TMEM) an issuer's loop has three pair times to complete.
+    const int NI = P.ni;
+    const int mw = warp == 1 ? 0 : (warp == 3 ? 1 : 2);
+    const int mw_next = mw + 1 == NI ? 0 : mw + 1;
     const uint32_t idesc = ptx::umma_idesc_bf16(128, P.NMMA);
     const uint64_t desc_hi = ptx::umma_desc_sw128(0, 1024) & 0xffffffff00000000ull;
     const uint32_t flags = uint32_t(ptx::umma_desc_sw128(0, 1024) & 0xffffffffull);
@@ -832,14 +837,15 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
     Ring st, dr;    // stage; ring slot of the first accumulator row of the current pair (tied to the absolute image row)
     SlotPhases fp;  // acc_free phases, one bit per slot pair (both issuers track every slot)
     uint32_t gp = 0, tok = 0;  // global pair sequence number; tokens consumed by this issuer
-    uint32_t prev_mask = 0;    // accumulator slot pairs claimed for pair gp - 1 (by the other issuer)
+    uint32_t pm1 = 0, pm2 = 0;  // accumulator slot pairs claimed for pairs gp - 1 and gp - 2 (other issuers' current pairs)
+    int turn = 0;               // gp mod NI
     ptx::mbar_wait(&w_full, 0);
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const Item it = decode_item(P, item);
       const int npairs = (it.h1 - it.h0 + 2 * PAD + 1) >> 1;
       dr.i = it.h0 % P.R;  // even: segments start at even rows, R is even
-      for (int pp = 0; pp < npairs; ++pp, ++gp) {
-        const bool mine = (gp & 1u) == uint32_t(mw);
+      for (int pp = 0; pp < npairs; ++pp, ++gp, turn = (turn + 1 == NI ? 0 : turn + 1)) {
+        const bool mine = turn == mw;
         int newest = dr.i + 2 * PAD;  // newest accumulator pair this input pair touches
         if (newest >= P.R) newest -= P.R;
         // slot pairs this input pair opens: the newest one, and at a segment start (3x3) also the segment's first
@@ -848,26 +854,28 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
         if (!mine) {
           fp.note(s1);
           if (s0 != s1) fp.note(s0);
-          prev_mask = cur_mask;
+          pm2 = pm1;
+          pm1 = cur_mask;
           for (int c = 0; c < P.nchunks; ++c) st.step(P.SA);
           dr.add(2, P.R);
           continue;
         }
-        // A slot may be claimed ahead of the token only if its previous use is older than the other issuer's current
-        // pair: otherwise that use's own claim may still be pending and a parity wait one phase ahead returns a false
+        // A slot may be claimed ahead of the token only if its previous use is older than the other issuers' current
+        // pairs: otherwise that use's own claim may still be pending and a parity wait one phase ahead returns a false
         // positive (ring positions jump at segment starts, so consecutive pairs can meet in one slot).
-        const uint32_t deferred = cur_mask & prev_mask;
+        const uint32_t deferred = cur_mask & (pm1 | (NI > 2 ? pm2 : 0u));
         if (!((deferred >> s1) & 1u)) fp.claim(acc_free, s1);
         if (s0 != s1 && !((deferred >> s0) & 1u)) fp.claim(acc_free, s0);
-        prev_mask = cur_mask;
+        pm2 = pm1;
+        pm1 = cur_mask;
         if (mw == 0 && lane == 0) STRACE(7, st.w * P.SA + st.i);
         uint32_t b0 = b_base;
         for (int c = 0; c < P.nchunks; ++c) {
           const int ksteps = c == P.nchunks - 1 ? klast : 4;
           // The first stage of a pair may be waited for ahead of the token only if its previous use lies before the
-          // other issuer's current pair (SA > nchunks): otherwise that use may not even be filled yet and a parity
-          // wait one phase ahead returns a false positive.
-          const bool late = c == 0 && gp > 0 && P.SA <= P.nchunks;
+          // other issuers' current pairs (SA > (NI-1) * nchunks): otherwise that use may not even be filled yet and a
+          // parity wait one phase ahead returns a false positive.
+          const bool late = c == 0 && gp > 0 && P.SA <= (NI - 1) * P.nchunks;
           if (!late) ptx::mbar_wait(&a_full[st.i], st.w & 1);
           if (c == 0 && gp > 0) {  // the other issuer's pair has completed
             ptx::mbar_wait(&mma_turn[mw], tok & 1u);
@@ -905,7 +913,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
             ptx::umma_commit(&a_empty[st.i]);
             if (c == P.nchunks - 1) {
               ptx::umma_commit(&acc_done[dr.i >> 1]);
-              ptx::umma_commit(&mma_turn[mw ^ 1]);
+              ptx::umma_commit(&mma_turn[mw_next]);
             }
             if (mw == 0) STRACE(4, st.w * P.SA + st.i);
           }
@@ -916,18 +924,20 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
         dr.add(2, P.R);
       }
       if (PAD) {  // the trailing accumulator-row pair of the segment receives no further input
-        if ((gp & 1u) == uint32_t(mw)) {
+        if (turn == mw) {
           ptx::mbar_wait(&mma_turn[mw], tok & 1u);  // gp > 0 here: every segment has at least one input pair
           ++tok;
           ptx::tc_fence_after_sync();
           if (ptx::elect_one()) {
             ptx::umma_commit(&acc_done[dr.i >> 1]);
-            ptx::umma_commit(&mma_turn[mw ^ 1]);
+            ptx::umma_commit(&mma_turn[mw_next]);
           }
           __syncwarp();
         }
-        prev_mask = 0;
+        pm2 = pm1;
+        pm1 = 0;
         ++gp;
+        turn = turn + 1 == NI ? 0 : turn + 1;
         dr.add(2, P.R);
       }
     }
@@ -1368,6 +1378,8 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   P.wbytes = uint32_t(kfold ? size_t(192) * 128 : (wide ? pk.wide_bytes : (rfold ? pk.rfold_bytes : pk.pass_bytes)));
   const int tail = 2 * P.nchunks * 64 * 4 + std::max(P.NT, 64) * 4 + 256 + (kfold ? kRawStages * kRawFloats * 4 + 128 : 0);
   if (gp && !rps2) return fail("conv_stream: group-planar input needs the two-row kernel (weights too large)");
+  static const int ni_env = getenv("CDAN_ISSUERS") ? atoi(getenv("CDAN_ISSUERS")) : 3;
+  P.ni = ni_env == 2 ? 2 : 3;
   P.stage_bytes = gp ? std::min(4, d.Cin / 16) * 8192 : 0;
   const int stage_bytes = gp ? P.stage_bytes : (rps2 ? 2 * kStage : kStage);
   P.SA = std::min(gp ? kMaxSA2 : kMaxSA, ((dual ? kSmemLimit2 : kSmemLimit) - 1024 - int(P.wbytes) - tail) / stage_bytes);

@@ -162,6 +162,52 @@ def test_host_buffer_pipeline_chunks(cuda_device, dtype):
     plan.set_option("host_chunk", 8)
 
 
+def test_host_buffer_pipeline_ramped_schedule(cuda_device):
+    """Batches of >= 2.5 chunks use a ramped schedule (chunk/4, chunk/2, full chunks, remainder, chunk/2, chunk/4): the
+    result must not depend on it."""
+    sd = stress_state_dict(77)
+    net = make_net(sd, "bf16", cuda_device)
+    plan = net.native_plan()
+    x = ramp_input(23, 16, 24, seed=3)
+    with torch.no_grad():
+        y_dev = net(x.to(cuda_device)).cpu()
+    for chunk in (4, 8):
+        plan.set_option("host_chunk", chunk)
+        assert torch.equal(plan.forward_host(x.pin_memory()), y_dev), chunk
+    plan.set_option("host_chunk", 8)
+
+
+_LAYOUT_AB = """
+import sys, hashlib, torch
+sys.path.insert(0, {pkg!r}); sys.path.insert(0, {root!r})
+from oracle.stress_init import stress_state_dict, ramp_input
+from models.cdan import CDAN
+net = CDAN().set_compute_dtype("bf16"); net.load_state_dict(stress_state_dict(5), strict=True)
+net = net.to("cuda:0").eval()
+with torch.no_grad():
+    y = net(ramp_input(2, 72, 264, seed=9).to("cuda:0")).cpu()
+print("HASH", hashlib.sha256(y.numpy().tobytes()).hexdigest())
+"""
+
+
+def test_final_dense_layouts_agree_bitwise(cuda_device):
+    """The final dense block runs on a group-planar concat buffer (one dense plane per 16 channels); CDAN_FD_PLANAR=0
+    keeps the NHWC buffer.  Both feed the same tcgen05 MMAs in the same order, so the outputs must be bitwise equal.
+    (The switch is read once per process, hence the two subprocesses.)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "multi-degradation-image-enhancement_b200")
+    code = _LAYOUT_AB.format(pkg=pkg, root=root)
+    hashes = []
+    for planar in ("1", "0"):
+        env = dict(os.environ, CDAN_FD_PLANAR=planar)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        hashes.append([l for l in out.stdout.splitlines() if l.startswith("HASH")][0])
+    assert hashes[0] == hashes[1]
+
+
 def test_full_size_1080p_properties(cuda_device):
     """BASELINE C3's image size (1920x1080, many column strips / row segments per image, every kernel form at its
     production geometry).  The CPU oracle needs ~15 s per 1080p image, so at this size parity is checked through
