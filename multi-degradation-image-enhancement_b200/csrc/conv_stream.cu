@@ -77,7 +77,9 @@ struct SParams {
   int R;         // ring slots (excluding the two shadow slots)
   int TW, strips, SEG, segs, nitems;
   int nchunks, nS, SA;
-  int ni;           // two-row kernel: number of MMA issuer warps (2 or 3)
+  int npc, gps;     // two-row kernel: stages per row pair; group-planar: 16-channel groups per stage (4, or 5 for Cin = 80)
+  int tok_inside;   // two-row kernel: the elected lane waits for the issuer token inside its issue region (A/B switch)
+  int ni, pt;       // two-row kernel: number of MMA issuer warps (2 or 3), row pairs per issuer turn (1 or 2)
   int stage_bytes;  // group-planar input only: bytes per two-row stage (8 KB per 16-channel group)
   int relu, sigmoid, Cout;
   uint32_t wbytes;
@@ -793,15 +795,15 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
       const int npairs = (it.h1 - it.h0 + 2 * PAD + 1) >> 1;
       for (int pp = 0; pp < npairs; ++pp) {
         const int j = it.h0 - PAD + 2 * pp;  // rows j, j+1: outside the image -> zero filled by TMA
-        for (int c = 0; c < P.nchunks; ++c) {
+        for (int c = 0; c < P.npc; ++c) {
           ptx::mbar_wait(&a_empty[st.i], (st.w & 1) ^ 1);
           if (ptx::elect_one()) {
             if (GP) {
-              const int ng = min(4, (P.Cin >> 4) - 4 * c);
+              const int ng = min(P.gps, (P.Cin >> 4) - P.gps * c);
               ptx::mbar_arrive_expect_tx(&raw_full[st.i], uint32_t(ng) * kGroupBytes);
               for (int g = 0; g < ng; ++g)
                 ptx::tma_load_4d(sA + size_t(st.i) * kStage2 + size_t(g) * kGroupBytes, &tmapA, 0, it.w0 - PAD, j,
-                                 it.n + (4 * c + g) * P.N, &raw_full[st.i]);
+                                 it.n + (P.gps * c + g) * P.N, &raw_full[st.i]);
             } else {
               ptx::mbar_arrive_expect_tx(&raw_full[st.i], kStage2);
               ptx::tma_load_4d(sA + size_t(st.i) * kStage2, &tmapA, c * 64, it.w0 - PAD, j, it.n, &raw_full[st.i]);
@@ -820,8 +822,10 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
     // (timeline traces in profiles/r01_trace_stream2.md).  Two issuers take alternate row pairs; the order of the
     // accumulations is kept by a token: an issuer starts its pair only after the other's MMAs have COMPLETED
     // (tcgen05.commit on mma_turn), so its hand-offs overlap the other's MMAs and results stay bitwise deterministic.
-    // With three issuers (warp 2 joins after allocating TMEM) an issuer's loop has three pair times to complete.
-    const int NI = P.ni;
+    // With three issuers (warp 2 joins after allocating TMEM) an issuer's loop has three pair times to complete, and a
+    // turn is P.pt consecutive pairs so that the hand-off latency (MMA completion + wake-up + fence) is paid once per
+    // P.pt pairs.
+    const int NI = P.ni, PT = P.pt, HIST = (NI - 1) * PT;  // HIST (<= 4) = pairs the other issuers may still be working on
     const int mw = warp == 1 ? 0 : (warp == 3 ? 1 : 2);
     const int mw_next = mw + 1 == NI ? 0 : mw + 1;
     const uint32_t idesc = ptx::umma_idesc_bf16(128, P.NMMA);
@@ -837,15 +841,20 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
     Ring st, dr;    // stage; ring slot of the first accumulator row of the current pair (tied to the absolute image row)
     SlotPhases fp;  // acc_free phases, one bit per slot pair (both issuers track every slot)
     uint32_t gp = 0, tok = 0;  // global pair sequence number; tokens consumed by this issuer
-    uint32_t pm1 = 0, pm2 = 0;  // accumulator slot pairs claimed for pairs gp - 1 and gp - 2 (other issuers' current pairs)
-    int turn = 0;               // gp mod NI
+    uint32_t pm1 = 0, pm2 = 0, pm3 = 0, pm4 = 0;  // accumulator slot pairs claimed for pairs gp-1 .. gp-4
+    int owner = 0, tpos = 0;                      // issuer of pair gp, position of gp inside that issuer's turn
+    auto next_pair = [&](uint32_t mask) {
+      pm4 = pm3; pm3 = pm2; pm2 = pm1; pm1 = mask;
+      ++gp;
+      if (++tpos == PT) { tpos = 0; owner = owner + 1 == NI ? 0 : owner + 1; }
+    };
     ptx::mbar_wait(&w_full, 0);
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const Item it = decode_item(P, item);
       const int npairs = (it.h1 - it.h0 + 2 * PAD + 1) >> 1;
       dr.i = it.h0 % P.R;  // even: segments start at even rows, R is even
-      for (int pp = 0; pp < npairs; ++pp, ++gp, turn = (turn + 1 == NI ? 0 : turn + 1)) {
-        const bool mine = turn == mw;
+      for (int pp = 0; pp < npairs; ++pp) {
+        const bool mine = owner == mw;
         int newest = dr.i + 2 * PAD;  // newest accumulator pair this input pair touches
         if (newest >= P.R) newest -= P.R;
         // slot pairs this input pair opens: the newest one, and at a segment start (3x3) also the segment's first
@@ -854,32 +863,35 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
         if (!mine) {
           fp.note(s1);
           if (s0 != s1) fp.note(s0);
-          pm2 = pm1;
-          pm1 = cur_mask;
-          for (int c = 0; c < P.nchunks; ++c) st.step(P.SA);
+          for (int c = 0; c < P.npc; ++c) st.step(P.SA);
           dr.add(2, P.R);
+          next_pair(cur_mask);
           continue;
         }
+        const bool first = tpos == 0, last = tpos == PT - 1;
+        const bool need_token = first && gp > 0;
         // A slot may be claimed ahead of the token only if its previous use is older than the other issuers' current
         // pairs: otherwise that use's own claim may still be pending and a parity wait one phase ahead returns a false
         // positive (ring positions jump at segment starts, so consecutive pairs can meet in one slot).
-        const uint32_t deferred = cur_mask & (pm1 | (NI > 2 ? pm2 : 0u));
+        // (Later pairs of a turn follow the token: everything before them is complete or this issuer's own.)
+        const uint32_t recent = pm1 | (HIST > 1 ? pm2 : 0u) | (HIST > 2 ? pm3 : 0u) | (HIST > 3 ? pm4 : 0u);
+        const uint32_t deferred = need_token ? (cur_mask & recent) : 0u;
         if (!((deferred >> s1) & 1u)) fp.claim(acc_free, s1);
         if (s0 != s1 && !((deferred >> s0) & 1u)) fp.claim(acc_free, s0);
-        pm2 = pm1;
-        pm1 = cur_mask;
         if (mw == 0 && lane == 0) STRACE(7, st.w * P.SA + st.i);
         uint32_t b0 = b_base;
-        for (int c = 0; c < P.nchunks; ++c) {
-          const int ksteps = c == P.nchunks - 1 ? klast : 4;
+        for (int c = 0; c < P.npc; ++c) {
+          const int ksteps = GP ? min(P.gps, (P.Cin >> 4) - P.gps * c) : (c == P.npc - 1 ? klast : 4);
           // The first stage of a pair may be waited for ahead of the token only if its previous use lies before the
-          // other issuers' current pairs (SA > (NI-1) * nchunks): otherwise that use may not even be filled yet and a
+          // other issuers' current pairs (SA > HIST * nchunks): otherwise that use may not even be filled yet and a
           // parity wait one phase ahead returns a false positive.
-          const bool late = c == 0 && gp > 0 && P.SA <= (NI - 1) * P.nchunks;
+          const bool late = c == 0 && need_token && P.SA <= HIST * P.npc;
           if (!late) ptx::mbar_wait(&a_full[st.i], st.w & 1);
-          if (c == 0 && gp > 0) {  // the other issuer's pair has completed
+          // Common case: the elected lane alone waits for the token, AFTER its descriptors are set up (the wait is the
+          // hand-off chain's critical path, everything hoisted above it is free).
+          const bool tok_inside = c == 0 && need_token && !late && deferred == 0u && P.tok_inside;
+          if (c == 0 && need_token && !tok_inside) {  // the previous issuer's turn has completed
             ptx::mbar_wait(&mma_turn[mw], tok & 1u);
-            ++tok;
             if (deferred) {
               if ((deferred >> s1) & 1u) fp.claim(acc_free, s1);
               if (s0 != s1 && ((deferred >> s0) & 1u)) fp.claim(acc_free, s0);
@@ -887,15 +899,25 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
           }
           if (late) ptx::mbar_wait(&a_full[st.i], st.w & 1);
           if (mw == 0 && lane == 0) STRACE(3, st.w * P.SA + st.i);
-          ptx::tc_fence_after_sync();
+          if (!tok_inside) ptx::tc_fence_after_sync();
           const uint32_t a0 = a_base + uint32_t(st.i) * (kStage2 >> 4);
+          const uint32_t tok_par = tok & 1u;
+          if (c == 0 && need_token) ++tok;
           if (ptx::elect_one()) {
             // One dynamic loop over the K=16 steps of the chunk, the (row, tap) MMAs of a step unrolled with immediate
             // descriptor offsets (a fully predicated 24-MMA unroll cost ~250 instructions per stage).
             const uint32_t dc0 = tmem_base + uint32_t(dr.i * P.SW);  // dr.i is even and R is even: no wrap inside a pair
-            uint32_t ak = a0, bk = b0;
+            uint32_t ak = a0;
+            if (tok_inside) {
+              ptx::mbar_wait(&mma_turn[mw], tok_par);
+              ptx::tc_fence_after_sync();
+            }
             if (!(P.ablate & 4)) {
-              for (int k = 0; k < ksteps; ++k, ak += a_k, bk += 2u) {
+              for (int k = 0; k < ksteps; ++k, ak += a_k) {
+                // weights are packed per 64-channel chunk; a group-planar stage may hold five groups (chunk 1, step 0)
+                const int gi = P.gps * c + k;
+                const uint32_t bk = GP ? b_base + uint32_t(gi >> 2) * (RFOLD ? 3u * blk16 : blk16) + uint32_t(gi & 3) * 2u
+                                       : b0 + 2u * uint32_t(k);
                 if (RFOLD) {
 #pragma unroll
                   for (int r = 0; r < 2; ++r)
@@ -911,9 +933,9 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
               }
             }
             ptx::umma_commit(&a_empty[st.i]);
-            if (c == P.nchunks - 1) {
+            if (c == P.npc - 1) {
               ptx::umma_commit(&acc_done[dr.i >> 1]);
-              ptx::umma_commit(&mma_turn[mw_next]);
+              if (last) ptx::umma_commit(&mma_turn[mw_next]);
             }
             if (mw == 0) STRACE(4, st.w * P.SA + st.i);
           }
@@ -922,23 +944,23 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
           b0 += RFOLD ? 3u * blk16 : blk16;
         }
         dr.add(2, P.R);
+        next_pair(cur_mask);
       }
       if (PAD) {  // the trailing accumulator-row pair of the segment receives no further input
-        if (turn == mw) {
-          ptx::mbar_wait(&mma_turn[mw], tok & 1u);  // gp > 0 here: every segment has at least one input pair
-          ++tok;
+        if (owner == mw) {
+          if (tpos == 0) {  // gp > 0 here: every segment has at least one input pair
+            ptx::mbar_wait(&mma_turn[mw], tok & 1u);
+            ++tok;
+          }
           ptx::tc_fence_after_sync();
           if (ptx::elect_one()) {
             ptx::umma_commit(&acc_done[dr.i >> 1]);
-            ptx::umma_commit(&mma_turn[mw_next]);
+            if (tpos == PT - 1) ptx::umma_commit(&mma_turn[mw_next]);
           }
           __syncwarp();
         }
-        pm2 = pm1;
-        pm1 = 0;
-        ++gp;
-        turn = turn + 1 == NI ? 0 : turn + 1;
         dr.add(2, P.R);
+        next_pair(0u);
       }
     }
   } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
@@ -1030,20 +1052,20 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
         const int npairs = (it.h1 - it.h0 + 2 * PAD + 1) >> 1;
         for (int pp = 0; pp < npairs; ++pp) {
           const int j = it.h0 - PAD + 2 * pp;
-          for (int c = 0; c < P.nchunks; ++c, turn ^= 1, st.step(P.SA)) {
+          for (int c = 0; c < P.npc; ++c, turn ^= 1, st.step(P.SA)) {
             if (turn != grp) continue;
-            const int ng = min(4, (P.Cin >> 4) - 4 * c);
+            const int ng = min(P.gps, (P.Cin >> 4) - P.gps * c);
             ptx::mbar_wait(&raw_full[st.i], st.w & 1);
             if ((aw & 7) == 0 && lane == 0) STRACE(1, st.w * P.SA + st.i);
             if (ok && !(P.ablate & 2)) {
               const uint32_t base = sA_u + uint32_t(st.i) * kStage2 + offp;
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
+              for (int g = 0; g < 5; ++g) {
                 if (g >= ng) break;
                 uint4 x[2];
 #pragma unroll
                 for (int r = 0; r < 2; ++r) x[r] = ptx::lds128(base + uint32_t(g) * kGroupBytes + uint32_t(r) * kGroupRow);
-                const uint4 csc = ptx::lds128(sc_u + uint32_t(c * 64 + g * 16) * 2u), csh = ptx::lds128(sh_u + uint32_t(c * 64 + g * 16) * 2u);
+                const uint4 csc = ptx::lds128(sc_u + uint32_t((P.gps * c + g) * 16) * 2u), csh = ptx::lds128(sh_u + uint32_t((P.gps * c + g) * 16) * 2u);
                 const __nv_bfloat162* gsc = reinterpret_cast<const __nv_bfloat162*>(&csc);
                 const __nv_bfloat162* gsh = reinterpret_cast<const __nv_bfloat162*>(&csh);
 #pragma unroll
@@ -1083,7 +1105,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
       const int npairs = (it.h1 - it.h0 + 2 * PAD + 1) >> 1;
       for (int pp = 0; pp < npairs; ++pp) {
         const int j = it.h0 - PAD + 2 * pp;
-        for (int c = 0; c < P.nchunks; ++c, turn ^= 1, st.step(P.SA)) {
+        for (int c = 0; c < P.npc; ++c, turn ^= 1, st.step(P.SA)) {
           if (turn != grp) continue;
           if (c != cached_c) {
             const float4 fs0 = *reinterpret_cast<const float4*>(s_pre_s + c * 64 + u * 8);
@@ -1380,7 +1402,14 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   if (gp && !rps2) return fail("conv_stream: group-planar input needs the two-row kernel (weights too large)");
   static const int ni_env = getenv("CDAN_ISSUERS") ? atoi(getenv("CDAN_ISSUERS")) : 3;
   P.ni = ni_env == 2 ? 2 : 3;
-  P.stage_bytes = gp ? std::min(4, d.Cin / 16) * 8192 : 0;
+  // two pairs per turn measured slower (the second pair's waits sit inside the token chain): 41.1 vs 40.1 ms per step
+  static const int pt_env = getenv("CDAN_PAIRS_PER_TURN") ? atoi(getenv("CDAN_PAIRS_PER_TURN")) : 1;
+  P.pt = pt_env == 2 ? 2 : 1;
+  static const int tok_env = getenv("CDAN_TOKEN_INSIDE") ? atoi(getenv("CDAN_TOKEN_INSIDE")) : 0;  // measured equal (39.0 vs 39.1 ms): off
+  P.tok_inside = tok_env != 0;
+  P.gps = gp ? (d.Cin == 80 ? 5 : std::min(4, d.Cin / 16)) : 4;  // the 80-channel transition fits one 40 KB stage per row pair
+  P.npc = gp ? ceil_div(d.Cin / 16, P.gps) : P.nchunks;
+  P.stage_bytes = gp ? P.gps * 8192 : 0;
   const int stage_bytes = gp ? P.stage_bytes : (rps2 ? 2 * kStage : kStage);
   P.SA = std::min(gp ? kMaxSA2 : kMaxSA, ((dual ? kSmemLimit2 : kSmemLimit) - 1024 - int(P.wbytes) - tail) / stage_bytes);
   // The two worker groups take alternate stages: with an even stage count every ring slot always belongs to the same
