@@ -8,8 +8,8 @@ PER GPU (BASELINE config C3's batch, the configuration the metric is quoted on; 
 weak scaling).  `value` = megapixels/s with inputs resident in HBM, device-timed (CUDA events, max over ranks);
 `e2e` = the same through the host-buffer C-ABI call (pinned host input -> H2D -> forward -> D2H) per step.
 `roofline` is for the tcgen05 convolutions (conv_stream_kernel + conv_umma_kernel, all conv launches of one step) against
-the measured bf16 peak; `roofline_dense` is for the single heaviest kernel, conv_stream2_kernel<4,0> (the 16 dense-block
-3x3 layers, ~36 % of the step), against the measured HBM bandwidth; `cpu_baseline` is the CPU oracle port timed on this
+the measured bf16 peak; `roofline_dense` is for the single heaviest kernel, conv_stream2_kernel<4,0,GP> (the 16 dense-block
+3x3 layers, ~33 % of the step), against the measured HBM bandwidth; `cpu_baseline` is the CPU oracle port timed on this
 box's host cores on a bounded sample.
 Inputs (796 MB per step) and activations are far larger than the 126 MB L2, so no explicit L2 flush is needed.
 `--impl reference` times the reference algorithm's CPU restatement (oracle/, the reference itself is a Python tree that
@@ -44,8 +44,8 @@ DENSE3X3 = {f"{blk}.layers.{l}": (c0 + 16 * l, div)
                                  ("decoder.final_dense", 3, 1)) for l in range(4)}
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per 32 x 1080p step from the `ncu --set full` capture
 # summarised in profiles/r01_allconv_ncu.md: the 16 dense-block 3x3 launches, and all 29 convolution launches.
-DENSE3X3_NCU_TRAFFIC_BYTES = 58469929000
-ALLCONV_NCU_TRAFFIC_BYTES = 98357771000
+DENSE3X3_NCU_TRAFFIC_BYTES = 53530252000
+ALLCONV_NCU_TRAFFIC_BYTES = 91306108000
 
 
 def measured_peaks():
@@ -298,7 +298,7 @@ def main():
         if dense_ms > 0:
             gbs = dense_bytes / (dense_ms * 1e-3) / 1e9
             line["roofline_dense"] = {
-                "bound": "hbm", "kernel": "conv_stream2_kernel<4,0> (16 dense-block 3x3 launches of a step)",
+                "bound": "hbm", "kernel": "conv_stream2_kernel<4,0,GP> (16 dense-block 3x3 launches of a step; GP=1 for the group-planar final dense block)",
                 "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                 "traffic": DENSE3X3_NCU_TRAFFIC_BYTES if (n, h, w) == (32, 1080, 1920) else None,
                 "algorithmic_bytes_per_step": dense_bytes, "kernel_ms_per_step": dense_ms,
