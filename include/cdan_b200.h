@@ -99,6 +99,10 @@ CDAN_API int cdan_op_upsample_add(int dtype, void* stream, const float* a, const
  * op: 0 enhance_contrast(contrast_factor), 1 enhance_color(saturation_factor), 2 sharpen(strength),
  * 3 soft_denoise(sigma).  x,y: fp32 [N,3,H,W]; in-place (x == y) allowed for ops 0 and 1. */
 CDAN_API int cdan_postprocess(void* stream, int op, float arg, const float* x, float* y, int N, int H, int W);
+/* Output quantisation of Model._save_batch_outputs (reference models/model.py:80-83, `(img*255).clip(0,255).astype(uint8)`
+ * after `permute(1,2,0)`): x fp32 [N,3,H,W] (device) -> y uint8 [N,H,W,3] (device), truncation toward zero.  H*W % 4 == 0.
+ * Stream-ordered; a quarter of the bytes of x then cross PCIe. */
+CDAN_API int cdan_quantize_u8(void* stream, const float* x, unsigned char* y, int N, int H, int W);
 /* PSNR and SSIM with torchmetrics' default settings (reference utils/metrics_factory.py:74-94); result_host[0] =
  * PSNR (dB), result_host[1] = SSIM.  Synchronises the stream. */
 CDAN_API int cdan_psnr_ssim(void* stream, const float* pred, const float* target, int N, int C, int H, int W,

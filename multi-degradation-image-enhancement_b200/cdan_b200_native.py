@@ -41,6 +41,7 @@ _PROTOTYPES = {
     "cdan_op_upsample_add": (_c_int, [_c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
                                       _c_void_p]),
     "cdan_postprocess": (_c_int, [_c_void_p, _c_int, _c_float, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
+    "cdan_quantize_u8": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
     "cdan_psnr_ssim": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
                                 ctypes.POINTER(_c_float)]),
 }
@@ -235,6 +236,20 @@ def postprocess(images: torch.Tensor, op: str, arg: float) -> torch.Tensor:
     with torch.cuda.device(dev):
         _check(lib().cdan_postprocess(_c_void_p(_stream(dev)), POSTPROC_OPS[op], float(arg), _ptr(x), _ptr(y), n, h, w),
                "postprocess")
+    return y
+
+
+def quantize_u8(images: torch.Tensor) -> torch.Tensor:
+    """[N,3,H,W] float (CUDA) -> [N,H,W,3] uint8 (CUDA): `(img * 255).clip(0, 255).astype(uint8)` of the reference's
+    _save_batch_outputs (models/model.py:80-83), on the device, so that only a quarter of the bytes cross PCIe."""
+    dev = images.device
+    x = _f32(images, dev)
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise RuntimeError("cdan_b200: quantize_u8 expects [N,3,H,W]")
+    n, _, h, w = x.shape
+    y = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib().cdan_quantize_u8(_c_void_p(_stream(dev)), _ptr(x), _ptr(y), n, h, w), "quantize_u8")
     return y
 
 

@@ -164,6 +164,12 @@ int cdan_postprocess(void* stream, int op, float arg, const float* x, float* y, 
   return 0;
 }
 
+int cdan_quantize_u8(void* stream, const float* x, unsigned char* y, int N, int H, int W) {
+  if (!x || !y) return fail("cdan_quantize_u8: NULL argument");
+  if (N <= 0 || H <= 0 || W <= 0) return fail("cdan_quantize_u8: empty input");
+  return quantize_u8_launch(x, y, N, H, W, (cudaStream_t)stream);
+}
+
 int cdan_psnr_ssim(void* stream, const float* pred, const float* target, int N, int C, int H, int W,
                    float* result_host2) {
   if (!pred || !target || !result_host2) return fail("cdan_psnr_ssim: NULL argument");

@@ -276,6 +276,35 @@ size_t metrics_scratch_floats(int planes, int H, int W) {
   return 1024 * 5 + 16 + tiles + 16;
 }
 
+// Output quantisation of Model._save_batch_outputs (reference models/model.py:80-83): planar fp32 [N,3,H,W] ->
+// interleaved uint8 [N,H,W,3], u8 = trunc(clip(x * 255, 0, 255)) exactly as numpy's `(img * 255).clip(0, 255).astype(uint8)`
+// (fp32 product, truncation toward zero).  One thread per four pixels: three coalesced float4 loads, three 32-bit stores.
+__global__ void __launch_bounds__(256) quantize_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, size_t HW,
+                                                           size_t quads_per_image, size_t total_quads) {
+  for (size_t q = blockIdx.x * size_t(blockDim.x) + threadIdx.x; q < total_quads; q += size_t(gridDim.x) * blockDim.x) {
+    const size_t n = q / quads_per_image, p = (q - n * quads_per_image) * 4;
+    const float* xi = x + n * 3 * HW + p;
+    const float4 r = *reinterpret_cast<const float4*>(xi), g = *reinterpret_cast<const float4*>(xi + HW),
+                 b = *reinterpret_cast<const float4*>(xi + 2 * HW);
+    auto cv = [](float v) -> uint32_t { return uint32_t(fminf(fmaxf(v * 255.0f, 0.0f), 255.0f)); };
+    const uint32_t px[12] = {cv(r.x), cv(g.x), cv(b.x), cv(r.y), cv(g.y), cv(b.y), cv(r.z), cv(g.z), cv(b.z), cv(r.w), cv(g.w), cv(b.w)};
+    uint32_t* o = reinterpret_cast<uint32_t*>(y + (n * HW + p) * 3);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o[i] = px[4 * i] | (px[4 * i + 1] << 8) | (px[4 * i + 2] << 16) | (px[4 * i + 3] << 24);
+  }
+}
+
+int quantize_u8_launch(const float* x, uint8_t* y, int N, int H, int W, cudaStream_t s) {
+  const size_t HW = size_t(H) * W;
+  if (HW % 4 != 0) return fail("quantize_u8: H*W must be a multiple of 4");
+  if (reinterpret_cast<uintptr_t>(x) % 16 != 0 || reinterpret_cast<uintptr_t>(y) % 4 != 0) return fail("quantize_u8: misaligned buffer");
+  const size_t qpi = HW / 4, total = qpi * N;
+  const int blocks = int(std::min<size_t>((total + 255) / 256, size_t(148) * 16));
+  quantize_u8_kernel<<<std::max(blocks, 1), 256, 0, s>>>(x, y, HW, qpi, total);
+  CDAN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int psnr_ssim_launch(const float* pred, const float* target, int N, int C, int H, int W, float* scratch, float* result,
                      cudaStream_t s) {
   const int planes = N * C;

@@ -72,7 +72,12 @@ class Model(BaseModel):
         out_dir = self.save_cfg.get("output_dir", "outputs/")
         os.makedirs(out_dir, exist_ok=True)
         fmt, resize_hw = self.save_cfg.get("format", "png"), self.save_cfg.get("resize_hw", None)
-        u8 = (outputs.detach() * 255).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().cpu().numpy()
+        outputs = outputs.detach()
+        if outputs.is_cuda and outputs.dim() == 4 and outputs.shape[1] == 3 and (outputs.shape[2] * outputs.shape[3]) % 4 == 0:
+            import cdan_b200_native as native  # quantise on the device: uint8 NHWC crosses PCIe, not fp32 NCHW
+            u8 = native.quantize_u8(outputs).cpu().numpy()
+        else:
+            u8 = (outputs * 255).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().cpu().numpy()
         for i, arr in enumerate(u8):
             img = Image.fromarray(np.ascontiguousarray(arr))
             if resize_hw is not None:

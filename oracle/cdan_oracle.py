@@ -232,6 +232,15 @@ def apply_postprocessing(images: torch.Tensor, pp_cfg: Optional[dict]) -> torch.
     return out
 
 
+def quantize_u8(images: torch.Tensor):
+    """Output quantisation of Model._save_batch_outputs (reference models/model.py:80-83): per image
+    `img = outputs[i].permute(1, 2, 0).numpy(); img = (img * 255).clip(0, 255).astype(np.uint8)` -> uint8 [N,H,W,3]
+    (fp32 product, truncation toward zero)."""
+    import numpy as np
+    x = images.detach().cpu().float()
+    return np.stack([(x[i].permute(1, 2, 0).numpy() * 255).clip(0, 255).astype(np.uint8) for i in range(x.shape[0])])
+
+
 def conv_flops_per_pixel() -> int:
     """Algorithmic conv FLOPs (2*MAC, unpadded) per input pixel; SURVEY A.1 = 252 770."""
     def c3(ci, co):

@@ -140,6 +140,23 @@ def test_postprocess_large_matches_oracle(cuda_device):
         assert (got - fn(x, arg)).abs().max() < 3e-6, op
 
 
+def test_quantize_u8_bit_exact(cuda_device):
+    """cdan_quantize_u8 against the reference's `(img * 255).clip(0, 255).astype(uint8)` (models/model.py:80-83): integer
+    output, so the bar is bit-exact — including the k/255 grid points, values just around them and out-of-range inputs."""
+    import cdan_b200_native as native
+    g = torch.Generator().manual_seed(17)
+    x = torch.rand((3, 3, 24, 40), generator=g) * 1.2 - 0.1          # some values below 0 and above 1
+    grid = torch.arange(256, dtype=torch.float32) / 255.0            # exact grid points and their fp32 neighbours
+    edge = torch.cat([grid, torch.nextafter(grid, torch.tensor(2.0)), torch.nextafter(grid, torch.tensor(-1.0))])
+    x.view(-1)[:edge.numel()] = edge
+    got = native.quantize_u8(x.to(cuda_device)).cpu().numpy()
+    want = O.quantize_u8(x)
+    assert got.dtype == np.uint8 and got.shape == (3, 24, 40, 3)
+    assert np.array_equal(got, want)
+    big = torch.rand((2, 3, 1080, 1920), generator=g)                # full-size frame
+    assert np.array_equal(native.quantize_u8(big.to(cuda_device)).cpu().numpy(), O.quantize_u8(big))
+
+
 def test_psnr_ssim_match_oracle(cuda_device):
     import cdan_b200_native as native
     g = torch.Generator().manual_seed(9)
