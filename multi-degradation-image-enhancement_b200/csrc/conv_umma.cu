@@ -427,6 +427,11 @@ int pick_nt(int Cout, int* npass) {
   if (Cout <= 32) return 32;
   if (Cout <= 64) return 64;
   if (Cout <= 128) return 128;
+  static const int nt_cap = getenv("CDAN_UMMA_NT") ? atoi(getenv("CDAN_UMMA_NT")) : 256;  // A/B switch: 128 = more M-blocks per weight pass
+  if (nt_cap == 128) {
+    *npass = (Cout + 127) / 128;
+    return 128;
+  }
   *npass = (Cout + 255) / 256;
   return 256;
 }
