@@ -18,6 +18,8 @@ struct ConvDesc {
   int ks = 3;               // 3 or 1
   const void* in = nullptr; // NHWC, storage type T
   int in_ld = 0;
+  const void* in2 = nullptr;  // hybrid concat buffer (Chead > 0): base of the group planes; `in`/`in_ld` describe the NHWC head
+  int Chead = 0;              // channels of the NHWC head (multiple of 64); 0 = all channels are in group planes
   size_t in_gstride = 0;    // bf16 tensor-core path only: if non-zero the input is GROUP-PLANAR — one dense plane
                             // [N][H][W][16] per 16-channel group, planes `in_gstride` elements apart, in_ld = 16
   const float* in_nchw = nullptr;  // if set: planar fp32 input [N][Cin][H][W] (first layer), `in` unused

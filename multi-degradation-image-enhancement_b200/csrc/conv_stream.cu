@@ -77,6 +77,8 @@ struct SParams {
   int R;         // ring slots (excluding the two shadow slots)
   int TW, strips, SEG, segs, nitems;
   int nchunks, nS, SA;
+  int wsplit;       // two-row kernel: both worker groups process every stage, one image row each (else alternate stages)
+  int nh, ngroups;  // two-row kernel: NHWC stages per row pair (hybrid: the head), planar 16-channel groups
   int npc, gps;     // two-row kernel: stages per row pair; group-planar: 16-channel groups per stage (4, or 5 for Cin = 80)
   int tok_inside;   // two-row kernel: the elected lane waits for the issuer token inside its issue region (A/B switch)
   int ni, pt;       // two-row kernel: number of MMA issuer warps (2 or 3), row pairs per issuer turn (1 or 2)
@@ -713,17 +715,27 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
 // SM; contiguous 32-byte lines merge into full 128-byte requests (profiles/r01_bulk_probe.log: 4.3-6.3 TB/s for one to
 // five groups).  One group = one K=16 MMA step: stage = [group][row][128 px x 32 B] in SWIZZLE_32B, the A descriptor of
 // tap s starts s pixels (s * 32 B) into the row.
-template <int FOLD, int EPI, bool GP>
-__global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_constant__ CUtensorMap tmapA, const SParams P) {
+// GP = 2 (hybrid): the buffer's head (the pooled ConvBlock output, P.nh 64-channel chunks) stays NHWC because the next
+// ConvBlock, the decoder skip connection and the stage taps read it as such; only the 16-channel groups the dense layers
+// append are planes.  A row pair then takes P.nh NHWC stages (tmapA) followed by planar stages of up to four groups
+// (tmapG); the weight image is indexed by 64-channel chunk either way.
+template <int FOLD, int EPI, int GP>
+__global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_constant__ CUtensorMap tmapA,
+                                                              const __grid_constant__ CUtensorMap tmapG, const SParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t kStage2 = GP ? uint32_t(P.stage_bytes) : uint32_t(2 * kStage);
+  const uint32_t kStage2 = GP == 1 ? uint32_t(P.stage_bytes) : uint32_t(2 * kStage);
   constexpr uint32_t kGroupBytes = 8192, kGroupRow = 4096;  // GP: two rows of one 16-channel group / one row
   uint8_t* sA = smem;
   uint8_t* sW = sA + size_t(P.SA) * kStage2 + 1024;
   float* s_pre_s = reinterpret_cast<float*>(sW + P.wbytes);
   float* s_pre_t = s_pre_s + P.nchunks * 64;
   float* s_bias = s_pre_t + P.nchunks * 64;
+  // BatchNorm scale / shift as bf16 tables (packed HFMA2 operands of the planar worker path), behind the bias vector
+  __nv_bfloat16* s_sc = reinterpret_cast<__nv_bfloat16*>(s_bias + 128);
+  __nv_bfloat16* s_sh = s_sc + P.nchunks * 64;
+  // stage c of a row pair is planar?  (GP 0: never, 1: always, 2: after the NHWC head)
+  auto planar_stage = [&](int c) { return GP == 1 || (GP == 2 && c >= P.nh); };
 
   __shared__ uint64_t a_full[kMaxSA2], a_empty[kMaxSA2], raw_full[kMaxSA2], acc_done[kMaxR / 2], acc_free[kMaxR / 2], w_full, mma_turn[3];
   __shared__ uint32_t tmem_base_s;
@@ -735,7 +747,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
 
   if (tid == 0) {
     for (int i = 0; i < kMaxSA2; ++i) {
-      ptx::mbar_init(&a_full[i], 8);
+      ptx::mbar_init(&a_full[i], P.wsplit ? 16 : 8);
       ptx::mbar_init(&a_empty[i], 1);
       ptx::mbar_init(&raw_full[i], 1);
     }
@@ -754,17 +766,16 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
     ptx::tmem_alloc(&tmem_base_s, 512);
     ptx::tmem_relinquish();
   }
-  // GP: BatchNorm scale / shift as bf16 tables (the workers' packed HFMA2 operands), in the space of the fp32 scale table
-  __nv_bfloat16* s_sc = reinterpret_cast<__nv_bfloat16*>(s_pre_s);
-  __nv_bfloat16* s_sh = s_sc + P.nchunks * 64;
   for (int i = tid; i < P.nchunks * 64; i += blockDim.x) {
     const bool ok = i < P.Cin;
-    if (GP) {
-      s_sc[i] = __float2bfloat16_rn(ok ? P.pre_s[i] : 0.f);
-      s_sh[i] = __float2bfloat16_rn(ok ? P.pre_t[i] : 0.f);
-    } else {
-      s_pre_s[i] = ok ? P.pre_s[i] : 0.f;
-      s_pre_t[i] = ok ? P.pre_t[i] : 0.f;
+    const float fs = ok ? P.pre_s[i] : 0.f, ft = ok ? P.pre_t[i] : 0.f;
+    if (GP != 0) {
+      s_sc[i] = __float2bfloat16_rn(fs);
+      s_sh[i] = __float2bfloat16_rn(ft);
+    }
+    if (GP != 1) {
+      s_pre_s[i] = fs;
+      s_pre_t[i] = ft;
     }
   }
   for (int i = tid; i < P.NT; i += blockDim.x) s_bias[i] = P.bias[i];
@@ -798,12 +809,13 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
         for (int c = 0; c < P.npc; ++c) {
           ptx::mbar_wait(&a_empty[st.i], (st.w & 1) ^ 1);
           if (ptx::elect_one()) {
-            if (GP) {
-              const int ng = min(P.gps, (P.Cin >> 4) - P.gps * c);
+            if (planar_stage(c)) {
+              const int g0 = P.gps * (c - P.nh);  // first group of this stage (groups count from the end of the head)
+              const int ng = min(P.gps, P.ngroups - g0);
               ptx::mbar_arrive_expect_tx(&raw_full[st.i], uint32_t(ng) * kGroupBytes);
               for (int g = 0; g < ng; ++g)
-                ptx::tma_load_4d(sA + size_t(st.i) * kStage2 + size_t(g) * kGroupBytes, &tmapA, 0, it.w0 - PAD, j,
-                                 it.n + (P.gps * c + g) * P.N, &raw_full[st.i]);
+                ptx::tma_load_4d(sA + size_t(st.i) * kStage2 + size_t(g) * kGroupBytes, GP == 2 ? &tmapG : &tmapA, 0,
+                                 it.w0 - PAD, j, it.n + (g0 + g) * P.N, &raw_full[st.i]);
             } else {
               ptx::mbar_arrive_expect_tx(&raw_full[st.i], kStage2);
               ptx::tma_load_4d(sA + size_t(st.i) * kStage2, &tmapA, c * 64, it.w0 - PAD, j, it.n, &raw_full[st.i]);
@@ -831,9 +843,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
     const uint32_t idesc = ptx::umma_idesc_bf16(128, P.NMMA);
     const uint64_t desc_hi = ptx::umma_desc_sw128(0, 1024) & 0xffffffff00000000ull;
     const uint32_t flags = uint32_t(ptx::umma_desc_sw128(0, 1024) & 0xffffffffull);
-    const uint64_t adesc_hi = GP ? (ptx::umma_desc_sw32(0, 256) & 0xffffffff00000000ull) : desc_hi;
-    const uint32_t a_row = GP ? (kGroupRow >> 4) : uint32_t(kStage >> 4);  // descriptor units (16 B) per image row
-    const uint32_t a_tap = GP ? 2u : 8u, a_k = GP ? (kGroupBytes >> 4) : 2u;  // per horizontal tap (one pixel) / per K=16 step
+    const uint64_t desc32_hi = ptx::umma_desc_sw32(0, 256) & 0xffffffff00000000ull;
     const uint32_t a_base = flags | ((ptx::smem_u32(sA) & 0x3FFFFu) >> 4);
     const uint32_t b_base = flags | ((ptx::smem_u32(sW) & 0x3FFFFu) >> 4);
     const uint32_t blk16 = uint32_t(P.NMMA) * 8u;
@@ -879,14 +889,26 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
         if (!((deferred >> s1) & 1u)) fp.claim(acc_free, s1);
         if (s0 != s1 && !((deferred >> s0) & 1u)) fp.claim(acc_free, s0);
         if (mw == 0 && lane == 0) STRACE(7, st.w * P.SA + st.i);
+        // With enough stages (SA >= NI*PT stages-per-pair: the previous use of every stage of this pair lies before the
+        // other issuers' current pairs) ALL stages of the pair are waited for ahead of the token, so that the chunk loop
+        // behind the token is pure MMA issue.
+        const bool early_all = need_token && P.npc > 1 && P.SA >= (HIST + PT) * P.npc;
+        if (early_all) {
+          Ring sx = st;
+          for (int c = 0; c < P.npc; ++c, sx.step(P.SA)) ptx::mbar_wait(&a_full[sx.i], sx.w & 1);
+        }
         uint32_t b0 = b_base;
         for (int c = 0; c < P.npc; ++c) {
-          const int ksteps = GP ? min(P.gps, (P.Cin >> 4) - P.gps * c) : (c == P.npc - 1 ? klast : 4);
+          const bool pl = planar_stage(c);
+          const int ksteps = pl ? min(P.gps, P.ngroups - P.gps * (c - P.nh)) : (GP == 2 || c != P.npc - 1 ? 4 : klast);
+          const uint64_t adesc_hi = pl ? desc32_hi : desc_hi;
+          const uint32_t a_row = pl ? (kGroupRow >> 4) : uint32_t(kStage >> 4);  // descriptor units (16 B) per image row
+          const uint32_t a_tap = pl ? 2u : 8u, a_k = pl ? (kGroupBytes >> 4) : 2u;  // per horizontal tap (one pixel) / per K=16 step
           // The first stage of a pair may be waited for ahead of the token only if its previous use lies before the
           // other issuers' current pairs (SA > HIST * nchunks): otherwise that use may not even be filled yet and a
           // parity wait one phase ahead returns a false positive.
           const bool late = c == 0 && need_token && P.SA <= HIST * P.npc;
-          if (!late) ptx::mbar_wait(&a_full[st.i], st.w & 1);
+          if (!late && !early_all) ptx::mbar_wait(&a_full[st.i], st.w & 1);
           // Common case: the elected lane alone waits for the token, AFTER its descriptors are set up (the wait is the
           // hand-off chain's critical path, everything hoisted above it is free).
           const bool tok_inside = c == 0 && need_token && !late && deferred == 0u && P.tok_inside;
@@ -916,8 +938,8 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
               for (int k = 0; k < ksteps; ++k, ak += a_k) {
                 // weights are packed per 64-channel chunk; a group-planar stage may hold five groups (chunk 1, step 0)
                 const int gi = P.gps * c + k;
-                const uint32_t bk = GP ? b_base + uint32_t(gi >> 2) * (RFOLD ? 3u * blk16 : blk16) + uint32_t(gi & 3) * 2u
-                                       : b0 + 2u * uint32_t(k);
+                const uint32_t bk = GP == 1 ? b_base + uint32_t(gi >> 2) * (RFOLD ? 3u * blk16 : blk16) + uint32_t(gi & 3) * 2u
+                                            : b0 + 2u * uint32_t(k);  // hybrid: four groups per planar stage = one chunk
                 if (RFOLD) {
 #pragma unroll
                   for (int r = 0; r < 2; ++r)
@@ -1038,55 +1060,11 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
     const int aw = warp - kWorkWarp0;
     const int grp = aw >> 3, t = (aw & 7) * 32 + lane, u = t & 7, qb = t >> 3;
     const uint32_t sA_u = ptx::smem_u32(sA);
-    if (GP) {
-      // thread <-> (pixel p, 16-byte half h) of every group row: SWIZZLE_32B swaps the halves of pixels with bit 2 set
-      const int p = t >> 1, h = t & 1;
-      const uint32_t offp = uint32_t(p) * 32u + (uint32_t((h ^ (p >> 2)) & 1) << 4);
-      const uint32_t sc_u = ptx::smem_u32(s_sc) + uint32_t(h) * 16u, sh_u = ptx::smem_u32(s_sh) + uint32_t(h) * 16u;
-      Ring st;
-      int turn = 0;
-      for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-        const Item it = decode_item(P, item);
-        const int col = it.w0 - PAD + p;
-        const bool ok = col >= 0 && col < P.W;
-        const int npairs = (it.h1 - it.h0 + 2 * PAD + 1) >> 1;
-        for (int pp = 0; pp < npairs; ++pp) {
-          const int j = it.h0 - PAD + 2 * pp;
-          for (int c = 0; c < P.npc; ++c, turn ^= 1, st.step(P.SA)) {
-            if (turn != grp) continue;
-            const int ng = min(P.gps, (P.Cin >> 4) - P.gps * c);
-            ptx::mbar_wait(&raw_full[st.i], st.w & 1);
-            if ((aw & 7) == 0 && lane == 0) STRACE(1, st.w * P.SA + st.i);
-            if (ok && !(P.ablate & 2)) {
-              const uint32_t base = sA_u + uint32_t(st.i) * kStage2 + offp;
-#pragma unroll
-              for (int g = 0; g < 5; ++g) {
-                if (g >= ng) break;
-                uint4 x[2];
-#pragma unroll
-                for (int r = 0; r < 2; ++r) x[r] = ptx::lds128(base + uint32_t(g) * kGroupBytes + uint32_t(r) * kGroupRow);
-                const uint4 csc = ptx::lds128(sc_u + uint32_t((P.gps * c + g) * 16) * 2u), csh = ptx::lds128(sh_u + uint32_t((P.gps * c + g) * 16) * 2u);
-                const __nv_bfloat162* gsc = reinterpret_cast<const __nv_bfloat162*>(&csc);
-                const __nv_bfloat162* gsh = reinterpret_cast<const __nv_bfloat162*>(&csh);
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                  __nv_bfloat162* v = reinterpret_cast<__nv_bfloat162*>(&x[r]);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) v[e] = __hfma2_relu(v[e], gsc[e], gsh[e]);
-                }
-#pragma unroll
-                for (int r = 0; r < 2; ++r)  // rows outside the image keep TMA's zero fill (padding after activation)
-                  if (j + r >= 0 && j + r < P.H) ptx::sts128(base + uint32_t(g) * kGroupBytes + uint32_t(r) * kGroupRow, x[r]);
-              }
-            }
-            ptx::fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&a_full[st.i]);
-            if ((aw & 7) == 0 && lane == 0) STRACE(2, st.w * P.SA + st.i);
-          }
-        }
-      }
-    } else {
+    // planar stages: thread <-> (pixel p, 16-byte half h) of every group row; SWIZZLE_32B swaps the halves of pixels with
+    // bit 2 set.  NHWC stages: thread <-> (16-byte channel unit u, pixels qb + 32*i) of both rows.
+    const int p = t >> 1, h = t & 1;
+    const uint32_t offp = uint32_t(p) * 32u + (uint32_t((h ^ (p >> 2)) & 1) << 4);
+    const uint32_t sc_u = ptx::smem_u32(s_sc) + uint32_t(h) * 16u, sh_u = ptx::smem_u32(s_sh) + uint32_t(h) * 16u;
     uint32_t off[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) off[i] = ptx::sw128_offset(uint32_t(qb + 32 * i), uint32_t(u));
@@ -1096,6 +1074,8 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
     int turn = 0;
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const Item it = decode_item(P, item);
+      const int colp = it.w0 - PAD + p;
+      const bool okp = colp >= 0 && colp < P.W;
       bool ok[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -1106,45 +1086,81 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
       for (int pp = 0; pp < npairs; ++pp) {
         const int j = it.h0 - PAD + 2 * pp;
         for (int c = 0; c < P.npc; ++c, turn ^= 1, st.step(P.SA)) {
-          if (turn != grp) continue;
-          if (c != cached_c) {
-            const float4 fs0 = *reinterpret_cast<const float4*>(s_pre_s + c * 64 + u * 8);
-            const float4 fs1 = *reinterpret_cast<const float4*>(s_pre_s + c * 64 + u * 8 + 4);
-            const float4 ft0 = *reinterpret_cast<const float4*>(s_pre_t + c * 64 + u * 8);
-            const float4 ft1 = *reinterpret_cast<const float4*>(s_pre_t + c * 64 + u * 8 + 4);
-            sc[0] = __floats2bfloat162_rn(fs0.x, fs0.y); sc[1] = __floats2bfloat162_rn(fs0.z, fs0.w);
-            sc[2] = __floats2bfloat162_rn(fs1.x, fs1.y); sc[3] = __floats2bfloat162_rn(fs1.z, fs1.w);
-            sh[0] = __floats2bfloat162_rn(ft0.x, ft0.y); sh[1] = __floats2bfloat162_rn(ft0.z, ft0.w);
-            sh[2] = __floats2bfloat162_rn(ft1.x, ft1.y); sh[3] = __floats2bfloat162_rn(ft1.z, ft1.w);
-            cached_c = c;
-          }
-          const bool active = u * 8 < min(64, P.Cin - c * 64);
-          ptx::mbar_wait(&raw_full[st.i], st.w & 1);
-          if (active) {
+          // wsplit: both groups work on every stage, one image row each (balanced whatever the mix of stage kinds, and
+          // every group observes every phase of every slot); else the groups take alternate stages
+          if (!P.wsplit && turn != grp) continue;
+          const int r_lo = P.wsplit ? grp : 0, r_hi = P.wsplit ? grp + 1 : 2;
+          if (planar_stage(c)) {
+            const int g0 = P.gps * (c - P.nh);
+            const int ng = min(P.gps, P.ngroups - g0);
+            ptx::mbar_wait(&raw_full[st.i], st.w & 1);
+            if ((aw & 7) == 0 && lane == 0) STRACE(1, st.w * P.SA + st.i);
+            if (okp && !(P.ablate & 2)) {
+              const uint32_t base = sA_u + uint32_t(st.i) * kStage2 + offp;
+              const uint32_t tab = uint32_t(P.nh * 64 + g0 * 16) * 2u;  // table offset of the stage's first channel
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              if (j + r < 0 || j + r >= P.H) continue;  // rows outside the image keep TMA's zero fill (padding after activation)
-              const uint32_t base = sA_u + uint32_t(st.i) * kStage2 + uint32_t(r) * kStage;
-              uint4 x[4];
+              for (int g = 0; g < 5; ++g) {
+                if (g >= ng) break;
+                uint4 x[2];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) x[i] = ptx::lds128(base + off[i]);
+                for (int r = 0; r < 2; ++r)
+                  if (r >= r_lo && r < r_hi) x[r] = ptx::lds128(base + uint32_t(g) * kGroupBytes + uint32_t(r) * kGroupRow);
+                const uint4 csc = ptx::lds128(sc_u + tab + uint32_t(g) * 32u), csh = ptx::lds128(sh_u + tab + uint32_t(g) * 32u);
+                const __nv_bfloat162* gsc = reinterpret_cast<const __nv_bfloat162*>(&csc);
+                const __nv_bfloat162* gsh = reinterpret_cast<const __nv_bfloat162*>(&csh);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                __nv_bfloat162* v = reinterpret_cast<__nv_bfloat162*>(&x[i]);
+                for (int r = 0; r < 2; ++r) {
+                  if (r < r_lo || r >= r_hi) continue;
+                  __nv_bfloat162* v = reinterpret_cast<__nv_bfloat162*>(&x[r]);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = __hfma2_relu(v[e], sc[e], sh[e]);
+                  for (int e = 0; e < 4; ++e) v[e] = __hfma2_relu(v[e], gsc[e], gsh[e]);
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r)  // rows outside the image keep TMA's zero fill (padding after activation)
+                  if (r >= r_lo && r < r_hi && j + r >= 0 && j + r < P.H) ptx::sts128(base + uint32_t(g) * kGroupBytes + uint32_t(r) * kGroupRow, x[r]);
               }
+            }
+          } else {
+            if (c != cached_c) {
+              const float4 fs0 = *reinterpret_cast<const float4*>(s_pre_s + c * 64 + u * 8);
+              const float4 fs1 = *reinterpret_cast<const float4*>(s_pre_s + c * 64 + u * 8 + 4);
+              const float4 ft0 = *reinterpret_cast<const float4*>(s_pre_t + c * 64 + u * 8);
+              const float4 ft1 = *reinterpret_cast<const float4*>(s_pre_t + c * 64 + u * 8 + 4);
+              sc[0] = __floats2bfloat162_rn(fs0.x, fs0.y); sc[1] = __floats2bfloat162_rn(fs0.z, fs0.w);
+              sc[2] = __floats2bfloat162_rn(fs1.x, fs1.y); sc[3] = __floats2bfloat162_rn(fs1.z, fs1.w);
+              sh[0] = __floats2bfloat162_rn(ft0.x, ft0.y); sh[1] = __floats2bfloat162_rn(ft0.z, ft0.w);
+              sh[2] = __floats2bfloat162_rn(ft1.x, ft1.y); sh[3] = __floats2bfloat162_rn(ft1.z, ft1.w);
+              cached_c = c;
+            }
+            const bool active = u * 8 < min(64, P.Cin - c * 64);
+            ptx::mbar_wait(&raw_full[st.i], st.w & 1);
+            if (active) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (ok[i]) ptx::sts128(base + off[i], x[i]);
+              for (int r = 0; r < 2; ++r) {
+                if (r < r_lo || r >= r_hi) continue;
+                if (j + r < 0 || j + r >= P.H) continue;  // rows outside the image keep TMA's zero fill (padding after activation)
+                const uint32_t base = sA_u + uint32_t(st.i) * kStage2 + uint32_t(r) * kStage;
+                uint4 x[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) x[i] = ptx::lds128(base + off[i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  __nv_bfloat162* v = reinterpret_cast<__nv_bfloat162*>(&x[i]);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) v[e] = __hfma2_relu(v[e], sc[e], sh[e]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (ok[i]) ptx::sts128(base + off[i], x[i]);
+              }
             }
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&a_full[st.i]);
+          if ((aw & 7) == 0 && lane == 0) STRACE(2, st.w * P.SA + st.i);
         }
       }
-    }
     }
   }
 
@@ -1315,7 +1331,8 @@ bool conv_stream_supported(const ConvDesc& d, const StreamPack& pk) {
   if (d.in_nchw) return pk.d_wk && d.Cin == 3 && d.W % 4 == 0 && d.relu && !d.pre_scale && !d.out_nchw && d.out_ld % 8 == 0 && (!d.pool || !((d.H | d.W) & 1));
   if (d.Cin % 8 != 0 || d.in_ld % 8 != 0) return false;
   if (d.in_gstride) {  // group-planar input: dense pre-activation layers of the two-row kernel only
-    if (!d.pre_scale || d.relu || d.pool || d.Cin % 16 != 0 || d.in_ld != 16) return false;
+    if (!d.pre_scale || d.relu || d.pool || d.Cin % 16 != 0) return false;
+    if (d.Chead ? (d.Chead % 64 != 0 || d.Chead >= d.Cin || !d.in2 || d.out_nchw) : d.in_ld != 16) return false;
     if (d.in_gstride != size_t(d.N) * d.H * d.W * 16) return false;  // planes must be contiguous (one tensor map)
     if (d.ks == 3) return pk.d_wr && !d.out_nchw && d.out_ld % 8 == 0;
     return pk.d_w && pk.NT > 0 && (d.out_nchw ? d.Cout <= 16 : d.out_ld % 8 == 0);
@@ -1370,10 +1387,10 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   // selects the one-row kernel (nine-tap fold) instead.
   static const int rps_env = getenv("CDAN_RPS") ? atoi(getenv("CDAN_RPS")) : 2;
   bool rps2 = false;
-  const bool gp = d.in_gstride != 0;
+  const int gp = d.in_gstride != 0 ? (d.Chead ? 2 : 1) : 0;  // 1 = group-planar input, 2 = NHWC head + group planes
   if ((rps_env != 1 || gp) && !dual && in_mode == kSPro && !d.pool) {
     const size_t wb = fold == 3 ? (pk.d_wr && !d.out_nchw ? pk.rfold_bytes : 0) : pk.pass_bytes;
-    const int tail2 = 2 * pk.nchunks * 64 * 4 + 128 * 4 + 256;
+    const int tail2 = 2 * pk.nchunks * 64 * 4 + 128 * 4 + 256 + 128 * 4 + pk.nchunks * 64 * 4;
     rps2 = wb > 0 && (kSmemLimit - 1024 - int(wb) - tail2) / (2 * kStage) >= 4;
   }
   static const char* dense_form = getenv("CDAN_DENSE_FORM");  // "rfold" | "shift" (A/B switch), default per layer
@@ -1398,7 +1415,8 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   P.in_nchw = d.in_nchw; P.pre_s = d.pre_scale; P.pre_t = d.pre_shift;
   P.out_ld = d.out_ld; P.out_nchw = d.out_nchw;
   P.wbytes = uint32_t(kfold ? size_t(192) * 128 : (wide ? pk.wide_bytes : (rfold ? pk.rfold_bytes : pk.pass_bytes)));
-  const int tail = 2 * P.nchunks * 64 * 4 + std::max(P.NT, 64) * 4 + 256 + (kfold ? kRawStages * kRawFloats * 4 + 128 : 0);
+  const int tail = 2 * P.nchunks * 64 * 4 + std::max(P.NT, 64) * 4 + 256 + (kfold ? kRawStages * kRawFloats * 4 + 128 : 0) +
+                   (rps2 ? 128 * 4 + P.nchunks * 64 * 4 : 0);  // two-row kernel: bf16 scale / shift tables behind a 128-float bias vector
   if (gp && !rps2) return fail("conv_stream: group-planar input needs the two-row kernel (weights too large)");
   static const int ni_env = getenv("CDAN_ISSUERS") ? atoi(getenv("CDAN_ISSUERS")) : 3;
   P.ni = ni_env == 2 ? 2 : 3;
@@ -1407,11 +1425,15 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   P.pt = pt_env == 2 ? 2 : 1;
   static const int tok_env = getenv("CDAN_TOKEN_INSIDE") ? atoi(getenv("CDAN_TOKEN_INSIDE")) : 0;  // measured equal (39.0 vs 39.1 ms): off
   P.tok_inside = tok_env != 0;
-  P.gps = gp ? (d.Cin == 80 ? 5 : std::min(4, d.Cin / 16)) : 4;  // the 80-channel transition fits one 40 KB stage per row pair
-  P.npc = gp ? ceil_div(d.Cin / 16, P.gps) : P.nchunks;
-  P.stage_bytes = gp ? P.gps * 8192 : 0;
-  const int stage_bytes = gp ? P.stage_bytes : (rps2 ? 2 * kStage : kStage);
-  P.SA = std::min(gp ? kMaxSA2 : kMaxSA, ((dual ? kSmemLimit2 : kSmemLimit) - 1024 - int(P.wbytes) - tail) / stage_bytes);
+  static const int ws_env = getenv("CDAN_WORKER_SPLIT") ? atoi(getenv("CDAN_WORKER_SPLIT")) : 0;  // measured slower (39.7 vs 38.8 ms per step): off
+  P.wsplit = ws_env != 0;
+  P.nh = gp == 2 ? d.Chead / 64 : 0;
+  P.ngroups = gp ? (d.Cin - d.Chead) / 16 : 0;
+  P.gps = gp == 1 ? (d.Cin == 80 ? 5 : std::min(4, d.Cin / 16)) : 4;  // the 80-channel transition fits one 40 KB stage per row pair
+  P.npc = gp ? P.nh + ceil_div(P.ngroups, P.gps) : P.nchunks;
+  P.stage_bytes = gp == 1 ? P.gps * 8192 : 0;
+  const int stage_bytes = gp == 1 ? P.stage_bytes : (rps2 ? 2 * kStage : kStage);
+  P.SA = std::min(gp == 1 ? kMaxSA2 : kMaxSA, ((dual ? kSmemLimit2 : kSmemLimit) - 1024 - int(P.wbytes) - tail) / stage_bytes);
   // The two worker groups take alternate stages: with an even stage count every ring slot always belongs to the same
   // group.  (With an odd count a group could test a slot's mbarrier parity a full phase ahead of the last phase it
   // observed there — parity waits then return a false positive and the pipeline desynchronises.)
@@ -1421,24 +1443,40 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   if (P.SA < 3) return fail("conv_stream: weights leave no room for the activation pipeline");
   const int smem_bytes = P.SA * stage_bytes + 1024 + int(P.wbytes) + tail + 1024;
 
-  CUtensorMap tmap;
+  CUtensorMap tmap, tmapG;
   std::memset(&tmap, 0, sizeof(tmap));
+  std::memset(&tmapG, 0, sizeof(tmapG));
   if (in_mode != kSNchw) {
     PFN_encodeTiled enc = stream_get_encode();
     if (!enc) return fail("conv_stream: cuTensorMapEncodeTiled is not available from the driver");
-    if (reinterpret_cast<uintptr_t>(d.in) % 16 != 0) return fail("conv_stream: input pointer must be 16-byte aligned");
-    // group-planar: the planes of all groups form one [N * groups][H][W][16] tensor, image n of group g = index n + g*N
-    cuuint64_t gdim[4] = {cuuint64_t(gp ? 16 : d.Cin), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(gp ? d.N * (d.Cin / 16) : d.N)};
-    cuuint64_t gstr[3] = {cuuint64_t(d.in_ld) * 2, cuuint64_t(d.W) * d.in_ld * 2, cuuint64_t(d.H) * d.W * d.in_ld * 2};
-    cuuint32_t box[4] = {cuuint32_t(gp ? 16 : 64), cuuint32_t(shift ? 32 : 128), cuuint32_t(rps2 ? 2 : 1), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.in), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, gp ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                     // 128-byte L2 promotion only when every K-chunk is a full 128-byte line; otherwise 64 bytes (ncu: with
-                     // promotion NONE a 32-byte line still pulled 128 bytes from DRAM, with 64B it pulls 64)
-                     (gp || d.Cin % 64 == 0) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail("conv_stream: cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
+    if (gp != 1) {  // NHWC input (gp 2: the head of a hybrid concat buffer)
+      if (reinterpret_cast<uintptr_t>(d.in) % 16 != 0) return fail("conv_stream: input pointer must be 16-byte aligned");
+      const int Cn = gp == 2 ? d.Chead : d.Cin;
+      cuuint64_t gdim[4] = {cuuint64_t(Cn), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.N)};
+      cuuint64_t gstr[3] = {cuuint64_t(d.in_ld) * 2, cuuint64_t(d.W) * d.in_ld * 2, cuuint64_t(d.H) * d.W * d.in_ld * 2};
+      cuuint32_t box[4] = {64, cuuint32_t(shift ? 32 : 128), cuuint32_t(rps2 ? 2 : 1), 1};
+      CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.in), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       // 128-byte L2 promotion only when every K-chunk is a full 128-byte line; otherwise 64 bytes (ncu:
+                       // with promotion NONE a 32-byte line still pulled 128 bytes from DRAM, with 64B it pulls 64)
+                       Cn % 64 == 0 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail("conv_stream: cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
+    }
+    if (gp) {
+      // group planes: the planes of all groups form one [N * groups][H][W][16] tensor, image n of group g = index n + g*N
+      const void* base = gp == 2 ? d.in2 : d.in;
+      if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return fail("conv_stream: plane pointer must be 16-byte aligned");
+      cuuint64_t gdim[4] = {16, cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.N) * cuuint64_t(P.ngroups)};
+      cuuint64_t gstr[3] = {32, cuuint64_t(d.W) * 32, cuuint64_t(d.H) * d.W * 32};
+      cuuint32_t box[4] = {16, 128, 2, 1};
+      CUresult r = enc(&tmapG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail("conv_stream: cuTensorMapEncodeTiled (planes) failed with code " + std::to_string(int(r)));
+      if (gp == 1) tmap = tmapG;
+    }
   }
   if (in_mode == kSNchw) {
     PFN_encodeTiled enc = stream_get_encode();
@@ -1482,12 +1520,20 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
       return 0;
     };
     int rc;
+    auto launch2 = [&](auto kern) -> int {
+      CDAN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      kern<<<grid, threads, smem_bytes, stream>>>(tmap, tmapG, P);
+      CDAN_CUDA_OK(cudaGetLastError());
+      return 0;
+    };
     if (rps2) {
-      if (gp) {
-        if (fold == 3) rc = launch(conv_stream2_kernel<4, kSStore, true>);
-        else rc = d.out_nchw ? launch(conv_stream2_kernel<1, kSNchwOut, true>) : launch(conv_stream2_kernel<1, kSStore, true>);
-      } else if (fold == 3) rc = launch(conv_stream2_kernel<4, kSStore, false>);
-      else rc = d.out_nchw ? launch(conv_stream2_kernel<1, kSNchwOut, false>) : launch(conv_stream2_kernel<1, kSStore, false>);
+      if (gp == 2) {
+        rc = fold == 3 ? launch2(conv_stream2_kernel<4, kSStore, 2>) : launch2(conv_stream2_kernel<1, kSStore, 2>);
+      } else if (gp == 1) {
+        if (fold == 3) rc = launch2(conv_stream2_kernel<4, kSStore, 1>);
+        else rc = d.out_nchw ? launch2(conv_stream2_kernel<1, kSNchwOut, 1>) : launch2(conv_stream2_kernel<1, kSStore, 1>);
+      } else if (fold == 3) rc = launch2(conv_stream2_kernel<4, kSStore, 0>);
+      else rc = d.out_nchw ? launch2(conv_stream2_kernel<1, kSNchwOut, 0>) : launch2(conv_stream2_kernel<1, kSStore, 0>);
     } else if (kfold) rc = d.pool ? launch(conv_stream_kernel<kSNchw, 3, kSPool>) : launch(conv_stream_kernel<kSNchw, 3, kSStore>);
     else if (fold == 3) {
       if (d.out_nchw) rc = in_mode == kSPro ? launch(conv_stream_kernel<kSPro, 3, kSNchwOut>) : launch(conv_stream_kernel<kSTma, 3, kSNchwOut>);

@@ -217,6 +217,12 @@ bool fd_planar_enabled() {
                         !(getenv("CDAN_CONV_STREAM") && atoi(getenv("CDAN_CONV_STREAM")) == 0);
   return v;
 }
+// CDAN_DENSE_HYBRID=0 keeps the concat buffers of dense blocks 1-3 NHWC (A/B switch).
+bool dense_hybrid_enabled() {
+  static const bool v = !(getenv("CDAN_DENSE_HYBRID") && atoi(getenv("CDAN_DENSE_HYBRID")) == 0) &&
+                        !(getenv("CDAN_CONV_STREAM") && atoi(getenv("CDAN_CONV_STREAM")) == 0);
+  return v;
+}
 int fd_ld() {
   static const int v = getenv("CDAN_FD_LD") ? atoi(getenv("CDAN_FD_LD")) : 128;
   return v;
@@ -306,12 +312,12 @@ int conv_dispatch(cdan_plan* p, const ConvLayer& L, const ConvDesc& d, cudaStrea
 
 int run_conv(cdan_plan* p, ConvId id, int N, int H, int W, const void* in, int in_ld, void* out, int out_ld,
              int pool, cudaStream_t s, const float* in_nchw = nullptr, float* out_nchw = nullptr, int sigmoid = 0,
-             size_t in_gstride = 0) {
+             size_t in_gstride = 0, const void* in2 = nullptr, int Chead = 0) {
   const ConvLayer& L = p->conv[id];
   ConvDesc d;
   d.N = N; d.H = H; d.W = W;
   d.Cin = L.Cin; d.Cout = L.Cout; d.ks = L.ks;
-  d.in = in; d.in_ld = in_ld; d.in_nchw = in_nchw; d.in_gstride = in_gstride;
+  d.in = in; d.in_ld = in_ld; d.in_nchw = in_nchw; d.in_gstride = in_gstride; d.in2 = in2; d.Chead = Chead;
   d.pre_scale = L.d_pre_s; d.pre_shift = L.d_pre_t;
   d.w = L.d_w; d.CoutP = L.CoutP; d.bias = L.d_bias;
   d.relu = L.relu; d.pool = pool;
@@ -354,6 +360,18 @@ int run_dense_planar(cdan_plan* p, ConvId first, int N, int h, int w, void* D, c
   return run_conv(p, ConvId(first + 4), N, h, w, D, 16, nullptr, 0, 0, s, nullptr, out_nchw, 1, gs);
 }
 
+// dense blocks 1-3 on a HYBRID concat buffer (bf16 tensor-core plans): the pooled ConvBlock output stays a compact NHWC
+// head of Cpre channels (the next ConvBlock, the decoder skip connection and the stage taps read it), the four 16-channel
+// groups the layers append are dense planes behind it.  Layer 0 reads only the head.
+int run_dense_hybrid(cdan_plan* p, ConvId first, int N, int h, int w, void* D, int Cpre, void* DN, cudaStream_t s) {
+  const size_t gs = size_t(N) * h * w * 16;
+  void* planes = at(D, size_t(N) * h * w * Cpre, p->dt);
+  CDAN_TRY(run_conv(p, first, N, h, w, D, Cpre, planes, 16, 0, s));
+  for (int l = 1; l < 4; ++l)
+    CDAN_TRY(run_conv(p, ConvId(first + l), N, h, w, D, Cpre, at(planes, gs * l, p->dt), 16, 0, s, nullptr, nullptr, 0, gs, planes, Cpre));
+  return run_conv(p, ConvId(first + 4), N, h, w, D, Cpre, DN, p->conv[first + 4].Cout, 0, s, nullptr, nullptr, 0, gs, planes, Cpre);
+}
+
 int run_cbam(cdan_plan* p, int slot, const void* x, const void* mul, void* out, int N, int h, int w, bool pooled,
              cudaStream_t s) {
   const CbamLayer& L = p->cbam[slot];
@@ -393,24 +411,30 @@ int forward_impl(cdan_plan* p, cudaStream_t s, const float* x, float* y, int N, 
 
   // ---- Encoder (models/cdan.py:70-98).  Pooled ConvBlock outputs land in channels [0,C) of the dense-block
   //      concat buffers, so they double as skip connections and as the first `features` entry.
-  CDAN_TRY(run_conv(p, ENC1, N, H, W, nullptr, 0, b.D1, 128, 1, s, x));
-  CDAN_TRY(run_dense(p, D1L0, N, H2, W2, b.D1, 128, 64, b.DN1, 64, s));
-  CDAN_TRY(run_conv(p, ENC2, N, H2, W2, b.D1, 128, b.D2, 192, 1, s));
-  CDAN_TRY(run_dense(p, D2L0, N, H4, W4, b.D2, 192, 128, b.DN2, 128, s));
-  CDAN_TRY(run_conv(p, ENC3, N, H4, W4, b.D2, 192, b.D3, 320, 1, s));
-  CDAN_TRY(run_dense(p, D3L0, N, H8, W8, b.D3, 320, 256, b.DN3, 256, s));
-  CDAN_TRY(run_conv(p, ENC4, N, H8, W8, b.D3, 320, b.E4, 512, 0, s));
+  // Concat buffers of dense blocks 1-3: hybrid (compact NHWC head + group planes) on the tensor-core path, else NHWC.
+  const bool hyb = dt == kBF16 && p->conv_impl == 0 && dense_hybrid_enabled();
+  const int ld1 = hyb ? 64 : 128, ld2 = hyb ? 128 : 192, ld3 = hyb ? 256 : 320;
+  CDAN_TRY(run_conv(p, ENC1, N, H, W, nullptr, 0, b.D1, ld1, 1, s, x));
+  if (hyb) CDAN_TRY(run_dense_hybrid(p, D1L0, N, H2, W2, b.D1, 64, b.DN1, s));
+  else CDAN_TRY(run_dense(p, D1L0, N, H2, W2, b.D1, 128, 64, b.DN1, 64, s));
+  CDAN_TRY(run_conv(p, ENC2, N, H2, W2, b.D1, ld1, b.D2, ld2, 1, s));
+  if (hyb) CDAN_TRY(run_dense_hybrid(p, D2L0, N, H4, W4, b.D2, 128, b.DN2, s));
+  else CDAN_TRY(run_dense(p, D2L0, N, H4, W4, b.D2, 192, 128, b.DN2, 128, s));
+  CDAN_TRY(run_conv(p, ENC3, N, H4, W4, b.D2, ld2, b.D3, ld3, 1, s));
+  if (hyb) CDAN_TRY(run_dense_hybrid(p, D3L0, N, H8, W8, b.D3, 256, b.DN3, s));
+  else CDAN_TRY(run_dense(p, D3L0, N, H8, W8, b.D3, 320, 256, b.DN3, 256, s));
+  CDAN_TRY(run_conv(p, ENC4, N, H8, W8, b.D3, ld3, b.E4, 512, 0, s));
   // ---- bottleneck CBAM(512) (models/cdan.py:173)
   CDAN_TRY(run_cbam(p, 0, b.E4, nullptr, b.B0, N, H8, W8, false, s));
   // ---- Decoder (models/cdan.py:126-159)
   CDAN_TRY(run_conv(p, DEC1, N, H8, W8, b.B0, 512, b.T1, 256, 0, s));
-  CDAN_TRY(run_up_add(p, 1, b.T1, 256, b.D3, 320, b.A1, N, H8, W8, 0, s));
+  CDAN_TRY(run_up_add(p, 1, b.T1, 256, b.D3, ld3, b.A1, N, H8, W8, 0, s));
   CDAN_TRY(run_cbam(p, 1, b.A1, b.DN3, b.C1, N, H8, W8, true, s));
   CDAN_TRY(run_conv(p, DEC2, N, H8, W8, b.C1, 256, b.T2, 128, 0, s));
-  CDAN_TRY(run_up_add(p, 2, b.T2, 128, b.D2, 192, b.U2, N, H4, W4, 1, s));
+  CDAN_TRY(run_up_add(p, 2, b.T2, 128, b.D2, ld2, b.U2, N, H4, W4, 1, s));
   CDAN_TRY(run_cbam(p, 2, b.U2, b.DN2, b.C2, N, H4, W4, true, s));
   CDAN_TRY(run_conv(p, DEC3, N, H4, W4, b.C2, 128, b.T3, 64, 0, s));
-  CDAN_TRY(run_up_add(p, 3, b.T3, 64, b.D1, 128, b.U3, N, H2, W2, 1, s));
+  CDAN_TRY(run_up_add(p, 3, b.T3, 64, b.D1, ld1, b.U3, N, H2, W2, 1, s));
   CDAN_TRY(run_cbam(p, 3, b.U3, b.DN1, b.C3, N, H2, W2, true, s));
   CDAN_TRY(run_conv(p, DEC4, N, H2, W2, b.C3, 64, b.T4, 8, 0, s));
   // The final dense block's concat buffer is group-planar on the tensor-core path, NHWC otherwise.
@@ -424,11 +448,11 @@ int forward_impl(cdan_plan* p, cudaStream_t s, const float* x, float* y, int N, 
 
   auto& st = p->stages;
   st.clear();
-  st["enc.out1"] = {b.D1, 64, 128, H2, W2};
+  st["enc.out1"] = {b.D1, 64, ld1, H2, W2};
   st["enc.dense1"] = {b.DN1, 64, 64, H2, W2};
-  st["enc.out2"] = {b.D2, 128, 192, H4, W4};
+  st["enc.out2"] = {b.D2, 128, ld2, H4, W4};
   st["enc.dense2"] = {b.DN2, 128, 128, H4, W4};
-  st["enc.out3"] = {b.D3, 256, 320, H8, W8};
+  st["enc.out3"] = {b.D3, 256, ld3, H8, W8};
   st["enc.dense3"] = {b.DN3, 256, 256, H8, W8};
   st["enc.conv4"] = {b.E4, 512, 512, H8, W8};
   st["bottleneck"] = {b.B0, 512, 512, H8, W8};
