@@ -44,8 +44,8 @@ DENSE3X3 = {f"{blk}.layers.{l}": (c0 + 16 * l, div)
                                  ("decoder.final_dense", 3, 1)) for l in range(4)}
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per 32 x 1080p step from the `ncu --set full` capture
 # summarised in profiles/r01_allconv_ncu.md: the 16 dense-block 3x3 launches, and all 29 convolution launches.
-DENSE3X3_NCU_TRAFFIC_BYTES = 53530252000
-ALLCONV_NCU_TRAFFIC_BYTES = 91306108000
+DENSE3X3_NCU_TRAFFIC_BYTES = 52028013000
+ALLCONV_NCU_TRAFFIC_BYTES = 89799143000
 
 
 def measured_peaks():
@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -78,9 +78,12 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None, t_load0=None):
+        """Summarise the samples received inside [t0, t1] (perf_counter; the timed region).  nvidia-smi needs ~0.2 s to
+        start, so it is launched before the warm-up; if the timed region is shorter than one sampling period the samples
+        taken under the same load during warm-up are used and the window says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -88,8 +91,13 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        rows = [r for ts, r in self.rows if t0 is None or (t0 <= ts <= t1 + 0.05)]
+        window = "timed region"
+        if not rows:
+            rows = [r for ts, r in self.rows if t_load0 is None or (t_load0 <= ts <= t1 + 0.05)]
+            window = "warm-up + timed region (same load)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -98,7 +106,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def synthetic_batch(n, h, w, seed=42):
@@ -204,6 +212,8 @@ def main():
     net = CDAN().set_compute_dtype(args.dtype)
     net.load_state_dict(default_state_dict(42))
     net = net.to(dev).eval()
+    sampler = ClockSampler(local_rank)  # started early: nvidia-smi needs a few hundred ms before its first sample
+    sampler.start()
     x_host = synthetic_batch(n, h, w, seed=42 + rank).pin_memory()
     y_host = torch.empty_like(x_host).pin_memory()
     x = x_host.to(dev)
@@ -216,7 +226,8 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    # ---- warm-up (also sizes the workspace)
+    # ---- warm-up (also sizes the workspace); the clock sampler is already streaming
+    t_warm0 = time.perf_counter()
     for _ in range(args.warmup):
         plan.forward(x, out=y)
     barrier()
@@ -224,16 +235,15 @@ def main():
     # ---- timed region: K forwards, inputs resident in HBM; per-launch CUDA-event spans recorded alongside
     plan.set_option("profile", 1)
     plan.profile_read()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_region0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
         plan.forward(x, out=y)
     ev1.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_region0, time.perf_counter(), t_warm0)
     ms_total = ev0.elapsed_time(ev1)
     spans = plan.profile_read()
     plan.set_option("profile", 0)
@@ -300,7 +310,7 @@ def main():
         if dense_ms > 0:
             gbs = dense_bytes / (dense_ms * 1e-3) / 1e9
             line["roofline_dense"] = {
-                "bound": "hbm", "kernel": "conv_stream2_kernel<4,0,GP> (16 dense-block 3x3 launches of a step; GP=1 for the group-planar final dense block)",
+                "bound": "hbm", "kernel": "conv_stream2_kernel<4,0,GP> (16 dense-block 3x3 launches of a step; GP=1 group-planar final dense block, GP=2 hybrid buffers of dense blocks 1-3)",
                 "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                 "traffic": DENSE3X3_NCU_TRAFFIC_BYTES if (n, h, w) == (32, 1080, 1920) else None,
                 "algorithmic_bytes_per_step": dense_bytes, "kernel_ms_per_step": dense_ms,

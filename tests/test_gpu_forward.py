@@ -190,22 +190,25 @@ print("HASH", hashlib.sha256(y.numpy().tobytes()).hexdigest())
 """
 
 
-def test_final_dense_layouts_agree_bitwise(cuda_device):
-    """The final dense block runs on a group-planar concat buffer (one dense plane per 16 channels); CDAN_FD_PLANAR=0
-    keeps the NHWC buffer.  Both feed the same tcgen05 MMAs in the same order, so the outputs must be bitwise equal.
-    (The switch is read once per process, hence the two subprocesses.)"""
+def test_layout_and_issuer_variants_agree_bitwise(cuda_device):
+    """Default build: the final dense block runs on a group-planar concat buffer, dense blocks 1-3 on hybrid buffers
+    (compact NHWC head + 16-channel group planes), three MMA issuer warps take row pairs round-robin.  The switches
+    CDAN_FD_PLANAR=0 / CDAN_DENSE_HYBRID=0 (NHWC buffers) and CDAN_ISSUERS=2 change memory layout and scheduling only:
+    every variant feeds the same tcgen05 MMAs in the same order, so the outputs must be bitwise equal.
+    (The switches are read once per process, hence the subprocesses.)"""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     pkg = os.path.join(root, "multi-degradation-image-enhancement_b200")
     code = _LAYOUT_AB.format(pkg=pkg, root=root)
-    hashes = []
-    for planar in ("1", "0"):
-        env = dict(os.environ, CDAN_FD_PLANAR=planar)
-        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    hashes = {}
+    for name, extra in (("default", {}), ("fd_nhwc", {"CDAN_FD_PLANAR": "0"}), ("dense_nhwc", {"CDAN_DENSE_HYBRID": "0"}),
+                        ("two_issuers", {"CDAN_ISSUERS": "2"})):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **extra), capture_output=True, text=True,
+                             timeout=600)
         assert out.returncode == 0, out.stderr[-2000:]
-        hashes.append([l for l in out.stdout.splitlines() if l.startswith("HASH")][0])
-    assert hashes[0] == hashes[1]
+        hashes[name] = [l for l in out.stdout.splitlines() if l.startswith("HASH")][0]
+    assert len(set(hashes.values())) == 1, hashes
 
 
 def test_full_size_1080p_properties(cuda_device):
