@@ -518,6 +518,71 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
             dp.skip(sl1);
             continue;
           }
+          if (kSplitPool) {
+            // Row-wise drain (wide pooled layers have one spare ring slot): the first row of the pair is read as soon as
+            // it is complete, kept as bf16(relu(v + bias)) in registers and its slot released at once; the second row is
+            // combined with it.  max() commutes with the monotone bias/ReLU/rounding chain, so the result is bitwise the
+            // same as pooling first.  Both groups drain every row, half of the channels each.
+            const bool row_ok = i >= it.h0 && i < it.h1;
+            const int cbeg = eg * (P.NT >> 1);
+            const bool odd = lane & 1;
+            bf16* o_row = P.out + ((size_t(it.n) * (P.H >> 1) + (i >> 1)) * (P.W >> 1) + (col >> 1)) * P.out_ld;
+            uint32_t held[4][8];  // up to 64 channels of row 0 as bf16 pairs
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const int sl = rr ? sl1 : sl0;
+              dp.wait(acc_done, sl);
+              ptx::tc_fence_after_sync();
+              if (rr == 0 && q == 0 && lane == 0) STRACE(5, sr.i >> 1);
+              const uint32_t tr = lb + uint32_t(sl * P.NT);
+#pragma unroll
+              for (int ci = 0; ci < 4; ++ci) {
+                const int c0 = cbeg + 16 * ci;
+                if (16 * ci >= (P.NT >> 1)) break;
+                uint32_t v[16];
+                if (row_ok) {
+                  ptx::tmem_ld16(tr + c0, v);
+                  ptx::tmem_wait_ld();
+                }
+                ptx::tmem_st16_zero(tr + c0);
+                if (!row_ok) continue;
+                uint32_t y[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float2 bb = *reinterpret_cast<const float2*>(s_bias + c0 + 2 * e);
+                  float f0 = __uint_as_float(v[2 * e]) + bb.x, f1 = __uint_as_float(v[2 * e + 1]) + bb.y;
+                  if (RELU) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+                  y[e] = bf2(f0, f1);
+                }
+                if (rr == 0) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) held[ci][e] = y[e];
+                } else {
+                  // vertical max, then the horizontal partner (lane ^ 1): even lane keeps channels [c0, c0+8), odd lane
+                  // [c0+8, c0+16) of the pooled pixel
+                  uint32_t m[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const __nv_bfloat162 lo = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&y[e]), *reinterpret_cast<const __nv_bfloat162*>(&held[ci][e]));
+                    const __nv_bfloat162 hi = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&y[4 + e]), *reinterpret_cast<const __nv_bfloat162*>(&held[ci][4 + e]));
+                    const uint32_t lo_u = *reinterpret_cast<const uint32_t*>(&lo), hi_u = *reinterpret_cast<const uint32_t*>(&hi);
+                    const uint32_t mine = odd ? hi_u : lo_u, theirs = odd ? lo_u : hi_u;
+                    const uint32_t got = __shfl_xor_sync(0xffffffffu, theirs, 1);
+                    const __nv_bfloat162 mm = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&mine), *reinterpret_cast<const __nv_bfloat162*>(&got));
+                    m[e] = *reinterpret_cast<const uint32_t*>(&mm);
+                  }
+                  const int cg = c0 + (odd ? 8 : 0);
+                  if (col_ok && cg < P.Cout && !(P.ablate & 1)) *reinterpret_cast<uint4*>(o_row + cg) = make_uint4(m[0], m[1], m[2], m[3]);
+                }
+              }
+              ptx::tmem_wait_st();
+              ptx::tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(&acc_free[sl]);
+            }
+            if (q == 0 && lane == 0) STRACE(6, sr.i >> 1);
+            continue;
+          }
           dp.wait(acc_done, sl0);
           dp.wait(acc_done, sl1);
           ptx::tc_fence_after_sync();
