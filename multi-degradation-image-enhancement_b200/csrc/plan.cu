@@ -612,13 +612,14 @@ int cdan_forward_host(cdan_plan* p, const float* x_host, float* y_host, int N, i
     p->host_stage_bytes = 4 * slot_floats * sizeof(float);
   }
   CDAN_TRY(ensure_workspace(p, cb, H, W));
-  // Chunk schedule: full chunks of `cb` images in the middle, a short ramp (cb/4, cb/2) at both ends so that the first
-  // forward starts after a quarter-chunk copy and only a quarter-chunk D2H copy trails the last forward.  Results do not
-  // depend on the schedule (the forward is batch-independent, bitwise).
+  // Chunk schedule: full chunks of `cb` images in the middle (large sub-batches run the kernels at their best rate), a
+  // short ramp (cb/8, 3cb/8) at both ends so that the first forward starts after an eighth-chunk copy and only an
+  // eighth-chunk D2H copy trails the last forward; each copy is hidden behind the forward of the neighbouring chunk.
+  // Results do not depend on the schedule (the forward is batch-independent, bitwise).
   std::vector<int> sched;
   {
     std::vector<int> ramp;
-    for (int c = std::max(1, cb / 4); c < cb; c *= 2) ramp.push_back(c);
+    for (int c = std::max(1, cb / 8); c < cb; c *= 3) ramp.push_back(c);
     int ramp_sum = 0;
     for (int c : ramp) ramp_sum += c;
     if (N >= 2 * ramp_sum + cb) {

@@ -75,7 +75,7 @@ struct cdan_plan {
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   float* host_stage = nullptr;  // [2 slots][x | y]
   size_t host_stage_bytes = 0;
-  int host_chunk = 8;           // images per pipeline step (option "host_chunk")
+  int host_chunk = 16;          // images per full pipeline step (option "host_chunk")
   // optional per-launch CUDA-event timing ("profile" option): label -> accumulated ms / count
   int profile = 0;
   struct Span { std::string label; cudaEvent_t e0, e1; };
