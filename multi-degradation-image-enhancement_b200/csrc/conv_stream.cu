@@ -149,6 +149,14 @@ struct SlotPhases {
     par ^= 1u << s;
   }
   __device__ __forceinline__ void skip(int s) { par ^= 1u << s; }  // a use observed by someone else
+  // same with the barrier array given as a 32-bit shared address (MMA issuers)
+  __device__ __forceinline__ void claim_a(uint32_t free_bars, int s) {
+    if ((used >> s) & 1u) {
+      ptx::mbar_wait_a(free_bars + 8u * uint32_t(s), (par >> s) & 1u);
+      par ^= 1u << s;
+    }
+    used |= 1u << s;
+  }
   // producer side, a use claimed by ANOTHER producer thread: same bookkeeping as claim() without the wait
   __device__ __forceinline__ void note(int s) {
     if ((used >> s) & 1u) par ^= 1u << s;
@@ -301,21 +309,23 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
       Ring st;        // A stage
       Ring dr;        // ring slot of the accumulator row this input row's window starts at
       SlotPhases fp;  // acc_free phases
+      const uint32_t a_full_u = ptx::smem_u32(a_full), a_empty_u = ptx::smem_u32(a_empty), acc_done_u = ptx::smem_u32(acc_done),
+                     acc_free_u = ptx::smem_u32(acc_free);
       ptx::mbar_wait(&w_full, 0);
       for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
         const Item it = decode_item(P, item);
         const int n_in = it.h1 - it.h0 + 2 * PAD;
         dr.i = it.h0 % P.R;  // accumulator row 0 of the segment = image row h0 - 2*PAD
         if (PAD) {           // the first input row also opens the segment's first two accumulator rows
-          fp.claim(acc_free, dr.i);
-          fp.claim(acc_free, dr.i + 1 == P.R ? 0 : dr.i + 1);
+          fp.claim_a(acc_free_u, dr.i);
+          fp.claim_a(acc_free_u, dr.i + 1 == P.R ? 0 : dr.i + 1);
         }
         for (int jj = 0; jj < n_in; ++jj) {
           const int j = it.h0 - PAD + jj;
           {
             int newest = dr.i + 2 * PAD;  // newest accumulator row this input row touches
             if (newest >= P.R) newest -= P.R;
-            fp.claim(acc_free, newest);
+            fp.claim_a(acc_free_u, newest);
           }
           ptx::tc_fence_after_sync();
           if (lane == 0) STRACE(7, dr.i);
@@ -324,7 +334,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
             uint32_t b0 = b_base;
             for (int c = 0; c < P.nchunks; ++c) {
               const int ksteps = c == P.nchunks - 1 ? klast : 4;
-              ptx::mbar_wait(&a_full[st.i], st.w & 1);
+              ptx::mbar_wait_a(a_full_u + 8u * uint32_t(st.i), st.w & 1);
               ptx::tc_fence_after_sync();
               if (lane == 0) STRACE(3, st.w * P.SA + st.i);
               const uint32_t a0 = a_base + uint32_t(st.i) * (kStage >> 4);
@@ -363,7 +373,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
                     if (k < ksteps)
                       ptx::umma_bf16(dcol, desc_hi | (a0 + uint32_t(2 * k)), desc_hi | (b0 + uint32_t(2 * k)), idesc, k == 0 ? acc0 : 1u);
                 }
-                ptx::umma_commit(&a_empty[st.i]);
+                ptx::umma_commit_a(a_empty_u + 8u * uint32_t(st.i));
               }
               if (lane == 0) STRACE(4, st.w * P.SA + st.i);
               __syncwarp();
@@ -371,15 +381,15 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
               b0 += WIDE ? 9u * blk16 : (RFOLD ? 3u * blk16 : blk16);
             }
           }
-          if (ptx::elect_one()) ptx::umma_commit(&acc_done[dr.i]);
+          if (ptx::elect_one()) ptx::umma_commit_a(acc_done_u + 8u * uint32_t(dr.i));
           __syncwarp();
           dr.step(P.R);
         }
         if (PAD) {  // the two trailing accumulator rows of the segment receive no further input
-          if (ptx::elect_one()) ptx::umma_commit(&acc_done[dr.i]);
+          if (ptx::elect_one()) ptx::umma_commit_a(acc_done_u + 8u * uint32_t(dr.i));
           __syncwarp();
           dr.step(P.R);
-          if (ptx::elect_one()) ptx::umma_commit(&acc_done[dr.i]);
+          if (ptx::elect_one()) ptx::umma_commit_a(acc_done_u + 8u * uint32_t(dr.i));
           __syncwarp();
           dr.step(P.R);
         }
@@ -923,6 +933,9 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
       ++gp;
       if (++tpos == PT) { tpos = 0; owner = owner + 1 == NI ? 0 : owner + 1; }
     };
+    const uint32_t a_full_u = ptx::smem_u32(a_full), a_empty_u = ptx::smem_u32(a_empty), acc_done_u = ptx::smem_u32(acc_done),
+                   acc_free_u = ptx::smem_u32(acc_free), my_turn_u = ptx::smem_u32(&mma_turn[mw]),
+                   next_turn_u = ptx::smem_u32(&mma_turn[mw_next]);
     ptx::mbar_wait(&w_full, 0);
     for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
       const Item it = decode_item(P, item);
@@ -951,8 +964,8 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
         // (Later pairs of a turn follow the token: everything before them is complete or this issuer's own.)
         const uint32_t recent = pm1 | (HIST > 1 ? pm2 : 0u) | (HIST > 2 ? pm3 : 0u) | (HIST > 3 ? pm4 : 0u);
         const uint32_t deferred = need_token ? (cur_mask & recent) : 0u;
-        if (!((deferred >> s1) & 1u)) fp.claim(acc_free, s1);
-        if (s0 != s1 && !((deferred >> s0) & 1u)) fp.claim(acc_free, s0);
+        if (!((deferred >> s1) & 1u)) fp.claim_a(acc_free_u, s1);
+        if (s0 != s1 && !((deferred >> s0) & 1u)) fp.claim_a(acc_free_u, s0);
         if (mw == 0 && lane == 0) STRACE(7, st.w * P.SA + st.i);
         // With enough stages (SA >= NI*PT stages-per-pair: the previous use of every stage of this pair lies before the
         // other issuers' current pairs) ALL stages of the pair are waited for ahead of the token, so that the chunk loop
@@ -960,7 +973,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
         const bool early_all = need_token && P.npc > 1 && P.SA >= (HIST + PT) * P.npc;
         if (early_all) {
           Ring sx = st;
-          for (int c = 0; c < P.npc; ++c, sx.step(P.SA)) ptx::mbar_wait(&a_full[sx.i], sx.w & 1);
+          for (int c = 0; c < P.npc; ++c, sx.step(P.SA)) ptx::mbar_wait_a(a_full_u + 8u * uint32_t(sx.i), sx.w & 1);
         }
         uint32_t b0 = b_base;
         for (int c = 0; c < P.npc; ++c) {
@@ -973,18 +986,18 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
           // other issuers' current pairs (SA > HIST * nchunks): otherwise that use may not even be filled yet and a
           // parity wait one phase ahead returns a false positive.
           const bool late = c == 0 && need_token && P.SA <= HIST * P.npc;
-          if (!late && !early_all) ptx::mbar_wait(&a_full[st.i], st.w & 1);
+          if (!late && !early_all) ptx::mbar_wait_a(a_full_u + 8u * uint32_t(st.i), st.w & 1);
           // Common case: the elected lane alone waits for the token, AFTER its descriptors are set up (the wait is the
           // hand-off chain's critical path, everything hoisted above it is free).
           const bool tok_inside = c == 0 && need_token && !late && deferred == 0u && P.tok_inside;
           if (c == 0 && need_token && !tok_inside) {  // the previous issuer's turn has completed
-            ptx::mbar_wait(&mma_turn[mw], tok & 1u);
+            ptx::mbar_wait_a(my_turn_u, tok & 1u);
             if (deferred) {
-              if ((deferred >> s1) & 1u) fp.claim(acc_free, s1);
-              if (s0 != s1 && ((deferred >> s0) & 1u)) fp.claim(acc_free, s0);
+              if ((deferred >> s1) & 1u) fp.claim_a(acc_free_u, s1);
+              if (s0 != s1 && ((deferred >> s0) & 1u)) fp.claim_a(acc_free_u, s0);
             }
           }
-          if (late) ptx::mbar_wait(&a_full[st.i], st.w & 1);
+          if (late) ptx::mbar_wait_a(a_full_u + 8u * uint32_t(st.i), st.w & 1);
           if (mw == 0 && lane == 0) STRACE(3, st.w * P.SA + st.i);
           if (!tok_inside) ptx::tc_fence_after_sync();
           const uint32_t a0 = a_base + uint32_t(st.i) * (kStage2 >> 4);
@@ -996,7 +1009,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
             const uint32_t dc0 = tmem_base + uint32_t(dr.i * P.SW);  // dr.i is even and R is even: no wrap inside a pair
             uint32_t ak = a0;
             if (tok_inside) {
-              ptx::mbar_wait(&mma_turn[mw], tok_par);
+              ptx::mbar_wait_a(my_turn_u, tok_par);
               ptx::tc_fence_after_sync();
             }
             if (!(P.ablate & 4)) {
@@ -1019,10 +1032,10 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
                 }
               }
             }
-            ptx::umma_commit(&a_empty[st.i]);
+            ptx::umma_commit_a(a_empty_u + 8u * uint32_t(st.i));
             if (c == P.npc - 1) {
-              ptx::umma_commit(&acc_done[dr.i >> 1]);
-              if (last) ptx::umma_commit(&mma_turn[mw_next]);
+              ptx::umma_commit_a(acc_done_u + 8u * uint32_t(dr.i >> 1));
+              if (last) ptx::umma_commit_a(next_turn_u);
             }
             if (mw == 0) STRACE(4, st.w * P.SA + st.i);
           }
@@ -1036,13 +1049,13 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
       if (PAD) {  // the trailing accumulator-row pair of the segment receives no further input
         if (owner == mw) {
           if (tpos == 0) {  // gp > 0 here: every segment has at least one input pair
-            ptx::mbar_wait(&mma_turn[mw], tok & 1u);
+            ptx::mbar_wait_a(my_turn_u, tok & 1u);
             ++tok;
           }
           ptx::tc_fence_after_sync();
           if (ptx::elect_one()) {
-            ptx::umma_commit(&acc_done[dr.i >> 1]);
-            if (tpos == PT - 1) ptx::umma_commit(&mma_turn[mw_next]);
+            ptx::umma_commit_a(acc_done_u + 8u * uint32_t(dr.i >> 1));
+            if (tpos == PT - 1) ptx::umma_commit_a(next_turn_u);
           }
           __syncwarp();
         }

@@ -107,6 +107,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   if (timed_out) mbar_timeout(bar, parity);
 }
+// Same with the barrier given as a 32-bit shared-window address: hot single-thread roles (MMA issuers) convert their
+// barrier arrays once — the generic->shared conversion (S2R + LEA) otherwise sits on the dependency chain of every wait.
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {
+  uint32_t timed_out;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .u32 cnt;\n\t"
+      "mov.u32 cnt, 0;\n\t"
+      "mov.u32 %0, 0;\n"
+      "CDAN_WAITA_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "@p bra CDAN_WAITA_DONE;\n\t"
+      "add.u32 cnt, cnt, 1;\n\t"
+      "setp.lt.u32 p, cnt, %4;\n\t"
+      "@p bra CDAN_WAITA_LOOP;\n\t"
+      "mov.u32 %0, 1;\n"
+      "CDAN_WAITA_DONE:\n\t"
+      "}"
+      : "=r"(timed_out)
+      : "r"(bar_addr), "r"(parity), "r"(CDAN_MBAR_SUSPEND_NS), "r"(CDAN_MBAR_MAX_POLLS)
+      : "memory");
+  if (timed_out) mbar_timeout(nullptr, parity | (bar_addr << 1));
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns = 64) {
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
