@@ -201,6 +201,10 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
   // Wide pooled layers (conv2: N = 128, four ring slots) leave the MMA warp one spare accumulator row, so MMA and
   // epilogue run back to back; both epilogue groups then drain EVERY row pair, half of the channels each.
   constexpr bool kSplitPool = WIDE && EPI == kSPool && kEG == 2;
+  // Pair-granular accumulator hand-offs for the other pooled layers (conv1): the epilogue consumes and releases row pairs
+  // (even slot, odd slot) as a unit, so acc_done is committed on the odd slot only and acc_free claimed / arrived on the
+  // even slot only — the issuing thread's per-row hand-offs are its critical path (one N=192 MMA per row).
+  constexpr bool kPairSync = EPI == kSPool && !kSplitPool;
 
   if (tid == 0) {
     for (int i = 0; i < kMaxSA; ++i) {
@@ -318,14 +322,14 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
         dr.i = it.h0 % P.R;  // accumulator row 0 of the segment = image row h0 - 2*PAD
         if (PAD) {           // the first input row also opens the segment's first two accumulator rows
           fp.claim_a(acc_free_u, dr.i);
-          fp.claim_a(acc_free_u, dr.i + 1 == P.R ? 0 : dr.i + 1);
+          if (!kPairSync) fp.claim_a(acc_free_u, dr.i + 1 == P.R ? 0 : dr.i + 1);
         }
         for (int jj = 0; jj < n_in; ++jj) {
           const int j = it.h0 - PAD + jj;
           {
             int newest = dr.i + 2 * PAD;  // newest accumulator row this input row touches
             if (newest >= P.R) newest -= P.R;
-            fp.claim_a(acc_free_u, newest);
+            if (!kPairSync || !(newest & 1)) fp.claim_a(acc_free_u, newest);
           }
           ptx::tc_fence_after_sync();
           if (lane == 0) STRACE(7, dr.i);
@@ -381,16 +385,22 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
               b0 += WIDE ? 9u * blk16 : (RFOLD ? 3u * blk16 : blk16);
             }
           }
-          if (ptx::elect_one()) ptx::umma_commit_a(acc_done_u + 8u * uint32_t(dr.i));
-          __syncwarp();
+          if (!kPairSync || (dr.i & 1)) {
+            if (ptx::elect_one()) ptx::umma_commit_a(acc_done_u + 8u * uint32_t(dr.i));
+            __syncwarp();
+          }
           dr.step(P.R);
         }
         if (PAD) {  // the two trailing accumulator rows of the segment receive no further input
-          if (ptx::elect_one()) ptx::umma_commit_a(acc_done_u + 8u * uint32_t(dr.i));
-          __syncwarp();
+          if (!kPairSync || (dr.i & 1)) {
+            if (ptx::elect_one()) ptx::umma_commit_a(acc_done_u + 8u * uint32_t(dr.i));
+            __syncwarp();
+          }
           dr.step(P.R);
-          if (ptx::elect_one()) ptx::umma_commit_a(acc_done_u + 8u * uint32_t(dr.i));
-          __syncwarp();
+          if (!kPairSync || (dr.i & 1)) {
+            if (ptx::elect_one()) ptx::umma_commit_a(acc_done_u + 8u * uint32_t(dr.i));
+            __syncwarp();
+          }
           dr.step(P.R);
         }
       }
@@ -524,7 +534,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
         for (int ii = 0; ii < n_acc; ii += 2, ++pairs_seen, sr.add(2, P.R), i += 2) {
           const int sl0 = sr.i, sl1 = sr.i + 1;  // h0 and R are even, so a pair never straddles the ring end
           if (!kSplitPool && kEG == 2 && (pairs_seen & 1) != eg) {
-            dp.skip(sl0);
+            if (!kPairSync) dp.skip(sl0);
             dp.skip(sl1);
             continue;
           }
@@ -593,7 +603,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
             if (q == 0 && lane == 0) STRACE(6, sr.i >> 1);
             continue;
           }
-          dp.wait(acc_done, sl0);
+          if (!kPairSync) dp.wait(acc_done, sl0);
           dp.wait(acc_done, sl1);
           ptx::tc_fence_after_sync();
           if (q == 0 && lane == 0) STRACE(5, sr.i >> 1);
@@ -657,7 +667,7 @@ __global__ void __launch_bounds__(32 * (kEpiWarp0 + epi_warps(IN) + work_warps(I
           __syncwarp();
           if (lane == 0) {
             ptx::mbar_arrive(&acc_free[sl0]);
-            ptx::mbar_arrive(&acc_free[sl1]);
+            if (!kPairSync) ptx::mbar_arrive(&acc_free[sl1]);
           }
           if (q == 0 && lane == 0) STRACE(6, sr.i >> 1);
         }
