@@ -938,6 +938,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
     uint32_t gp = 0, tok = 0;  // global pair sequence number; tokens consumed by this issuer
     uint32_t pm1 = 0, pm2 = 0, pm3 = 0, pm4 = 0;  // accumulator slot pairs claimed for pairs gp-1 .. gp-4
     int owner = 0, tpos = 0;                      // issuer of pair gp, position of gp inside that issuer's turn
+    bool nx_claimed = false, nx_waited = false;   // PT = 2: the turn's second pair was claimed / its stages awaited early
     auto next_pair = [&](uint32_t mask) {
       pm4 = pm3; pm3 = pm2; pm2 = pm1; pm1 = mask;
       ++gp;
@@ -974,8 +975,30 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
         // (Later pairs of a turn follow the token: everything before them is complete or this issuer's own.)
         const uint32_t recent = pm1 | (HIST > 1 ? pm2 : 0u) | (HIST > 2 ? pm3 : 0u) | (HIST > 3 ? pm4 : 0u);
         const uint32_t deferred = need_token ? (cur_mask & recent) : 0u;
-        if (!((deferred >> s1) & 1u)) fp.claim_a(acc_free_u, s1);
-        if (s0 != s1 && !((deferred >> s0) & 1u)) fp.claim_a(acc_free_u, s0);
+        const bool pre_c = !first && nx_claimed, pre_w = !first && nx_waited;  // done while waiting for this turn's token
+        nx_claimed = nx_waited = false;
+        if (!pre_c) {
+          if (!((deferred >> s1) & 1u)) fp.claim_a(acc_free_u, s1);
+          if (s0 != s1 && !((deferred >> s0) & 1u)) fp.claim_a(acc_free_u, s0);
+        }
+        if (PT == 2 && first && pp + 1 < npairs) {
+          // Two pairs per turn: the second pair's accumulator slot and stages are serviced here, ahead of the token, under
+          // the same two rules (slot not claimed for the other issuers' current pairs; previous use of its stages older
+          // than those pairs) — behind the token the turn is then pure MMA issue for both pairs.
+          int nn = dr.i + 2 + 2 * PAD;
+          while (nn >= P.R) nn -= P.R;
+          const uint32_t mn = 1u << (nn >> 1);
+          if (!need_token || !(mn & (recent | cur_mask))) {
+            fp.claim_a(acc_free_u, nn >> 1);
+            nx_claimed = true;
+          }
+          if (!need_token || P.SA >= (HIST + PT) * P.npc) {
+            Ring sx = st;
+            for (int c = 0; c < P.npc; ++c) sx.step(P.SA);
+            for (int c = 0; c < P.npc; ++c, sx.step(P.SA)) ptx::mbar_wait_a(a_full_u + 8u * uint32_t(sx.i), sx.w & 1);
+            nx_waited = true;
+          }
+        }
         if (mw == 0 && lane == 0) STRACE(7, st.w * P.SA + st.i);
         // With enough stages (SA >= NI*PT stages-per-pair: the previous use of every stage of this pair lies before the
         // other issuers' current pairs) ALL stages of the pair are waited for ahead of the token, so that the chunk loop
@@ -996,7 +1019,7 @@ __global__ void __launch_bounds__(896, 1) conv_stream2_kernel(const __grid_const
           // other issuers' current pairs (SA > HIST * nchunks): otherwise that use may not even be filled yet and a
           // parity wait one phase ahead returns a false positive.
           const bool late = c == 0 && need_token && P.SA <= HIST * P.npc;
-          if (!late && !early_all) ptx::mbar_wait_a(a_full_u + 8u * uint32_t(st.i), st.w & 1);
+          if (!late && !early_all && !pre_w) ptx::mbar_wait_a(a_full_u + 8u * uint32_t(st.i), st.w & 1);
           // Common case: the elected lane alone waits for the token, AFTER its descriptors are set up (the wait is the
           // hand-off chain's critical path, everything hoisted above it is free).
           const bool tok_inside = c == 0 && need_token && !late && deferred == 0u && P.tok_inside;
@@ -1509,8 +1532,8 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   static const int ni_env = getenv("CDAN_ISSUERS") ? atoi(getenv("CDAN_ISSUERS")) : 3;
   P.ni = ni_env == 2 ? 2 : 3;
   // two pairs per turn measured slower (the second pair's waits sit inside the token chain): 41.1 vs 40.1 ms per step
-  static const int pt_env = getenv("CDAN_PAIRS_PER_TURN") ? atoi(getenv("CDAN_PAIRS_PER_TURN")) : 1;
-  P.pt = pt_env == 2 ? 2 : 1;
+  static const int pt_env = getenv("CDAN_PAIRS_PER_TURN") ? atoi(getenv("CDAN_PAIRS_PER_TURN")) : 0;
+  P.pt = pt_env == 2 ? 2 : 1;  // 3: adaptive, chosen below once the stage count is known
   static const int tok_env = getenv("CDAN_TOKEN_INSIDE") ? atoi(getenv("CDAN_TOKEN_INSIDE")) : 0;  // measured equal (39.0 vs 39.1 ms): off
   P.tok_inside = tok_env != 0;
   static const int ws_env = getenv("CDAN_WORKER_SPLIT") ? atoi(getenv("CDAN_WORKER_SPLIT")) : 0;  // measured slower (39.7 vs 38.8 ms per step): off
@@ -1529,6 +1552,10 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   static const int sa_cap = getenv("CDAN_SA_MAX") ? atoi(getenv("CDAN_SA_MAX")) : kMaxSA;
   P.SA = std::min(P.SA, std::max(3, sa_cap));
   if (P.SA < 3) return fail("conv_stream: weights leave no room for the activation pipeline");
+  // CDAN_PAIRS_PER_TURN=3: two row pairs per issuer turn where the stage ring is deep enough for both pairs' stages to
+  // be awaited ahead of the token (SA >= issuers * 2 * stages per pair).  Measured slower than one pair per turn even so
+  // (final dense layers 1.45/1.56/1.79/2.16 -> 1.54/1.82/2.10/2.40 ms), hence not the default.
+  if (pt_env == 3) P.pt = (rps2 && P.SA >= P.ni * 2 * P.npc) ? 2 : 1;
   const int smem_bytes = P.SA * stage_bytes + 1024 + int(P.wbytes) + tail + 1024;
 
   CUtensorMap tmap, tmapG;
