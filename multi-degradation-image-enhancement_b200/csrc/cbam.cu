@@ -294,10 +294,11 @@ int cbam_typed(const void* x, int x_ld, const void* mul, int mul_ld, void* out, 
   const size_t npix = size_t(N) * HW;
   const int lpp = vecs < 32 ? vecs : 32;
   if (C <= 512) {  // lanes cover the channels of a pixel in at most two 16-byte vectors each
-    constexpr int U = 4;
+    // pixels per lane and iteration: 4 with one vector per lane, 2 with two (C = 512); 8 / 4 measured slower
+    const int U = vecs <= 32 ? 4 : 2;
     const int ppw = 32 / lpp, bx = std::max(1, std::min(ceil_div(HW, 8 * ppw * U), ceil_div(148 * 8, N)));
-    if (vecs <= 32) compress2_kernel<T, 1, U><<<dim3(bx, N), 256, 0, s>>>((const T*)x, x_ld, C, HW, sc.gate, sc.comp);
-    else compress2_kernel<T, 2, U><<<dim3(bx, N), 256, 0, s>>>((const T*)x, x_ld, C, HW, sc.gate, sc.comp);
+    if (vecs <= 32) compress2_kernel<T, 1, 4><<<dim3(bx, N), 256, 0, s>>>((const T*)x, x_ld, C, HW, sc.gate, sc.comp);
+    else compress2_kernel<T, 2, 2><<<dim3(bx, N), 256, 0, s>>>((const T*)x, x_ld, C, HW, sc.gate, sc.comp);
   } else {
     compress_kernel<T><<<grid_for(npix * lpp), 256, 0, s>>>((const T*)x, x_ld, C, HW, npix, sc.gate, sc.comp);
   }
