@@ -34,6 +34,18 @@ __global__ void __launch_bounds__(256) up_add_kernel(const T* __restrict__ a, in
   float s[8], m[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { s[e] = 0.f; m[e] = -INFINITY; }
+  auto emit_sk = [&](int oy, int ox, F8 r, const F8& sk) {  // skip value loaded ahead by the caller
+    const size_t pix = (size_t(n) * OH + oy) * OW + ox;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r.v[e] += sk.v[e];
+    store8<T>(out + pix * out_ld + v * 8, r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float q = to_f32<T>(from_f32<T>(r.v[e]));  // pool what was stored
+      s[e] += q;
+      m[e] = fmaxf(m[e], q);
+    }
+  };
   auto emit = [&](int oy, int ox, F8 r) {
     const size_t pix = (size_t(n) * OH + oy) * OW + ox;
     const F8 sk = load8<T>(skip + pix * skip_ld + v * 8);
@@ -54,29 +66,33 @@ __global__ void __launch_bounds__(256) up_add_kernel(const T* __restrict__ a, in
         const int jm = max(j - 1, 0), jp = min(j + 1, IH - 1), im = max(i - 1, 0), ip = min(i + 1, IW - 1);
         const F8 m0 = load8<T>(an + (size_t(j) * IW + im) * a_ld), m1 = load8<T>(an + (size_t(j) * IW + i) * a_ld),
                  m2 = load8<T>(an + (size_t(j) * IW + ip) * a_ld);
+        // all four skip vectors of the quad are requested before any arithmetic (one latency instead of four)
+        const T* sq = skip + ((size_t(n) * OH + 2 * j) * OW + 2 * i) * skip_ld + v * 8;
+        const F8 k00 = load8<T>(sq), k01 = load8<T>(sq + skip_ld), k10 = load8<T>(sq + size_t(OW) * skip_ld),
+                 k11 = load8<T>(sq + size_t(OW) * skip_ld + skip_ld);
+        const F8 t0 = load8<T>(an + (size_t(jm) * IW + im) * a_ld), t1 = load8<T>(an + (size_t(jm) * IW + i) * a_ld),
+                 t2 = load8<T>(an + (size_t(jm) * IW + ip) * a_ld);
+        const F8 b0 = load8<T>(an + (size_t(jp) * IW + im) * a_ld), b1 = load8<T>(an + (size_t(jp) * IW + i) * a_ld),
+                 b2 = load8<T>(an + (size_t(jp) * IW + ip) * a_ld);
         {
-          const F8 t0 = load8<T>(an + (size_t(jm) * IW + im) * a_ld), t1 = load8<T>(an + (size_t(jm) * IW + i) * a_ld),
-                   t2 = load8<T>(an + (size_t(jm) * IW + ip) * a_ld);
           F8 r0, r1;
 #pragma unroll
           for (int e = 0; e < 8; ++e) {  // row 2j: rows (j-1: .25, j: .75); cols even (i-1: .25, i: .75), odd (i: .75, i+1: .25)
             r0.v[e] = 0.25f * (0.25f * t0.v[e] + 0.75f * t1.v[e]) + 0.75f * (0.25f * m0.v[e] + 0.75f * m1.v[e]);
             r1.v[e] = 0.25f * (0.75f * t1.v[e] + 0.25f * t2.v[e]) + 0.75f * (0.75f * m1.v[e] + 0.25f * m2.v[e]);
           }
-          emit(2 * j, 2 * i, r0);
-          emit(2 * j, 2 * i + 1, r1);
+          emit_sk(2 * j, 2 * i, r0, k00);
+          emit_sk(2 * j, 2 * i + 1, r1, k01);
         }
         {
-          const F8 b0 = load8<T>(an + (size_t(jp) * IW + im) * a_ld), b1 = load8<T>(an + (size_t(jp) * IW + i) * a_ld),
-                   b2 = load8<T>(an + (size_t(jp) * IW + ip) * a_ld);
           F8 r0, r1;
 #pragma unroll
           for (int e = 0; e < 8; ++e) {  // row 2j+1: rows (j: .75, j+1: .25)
             r0.v[e] = 0.75f * (0.25f * m0.v[e] + 0.75f * m1.v[e]) + 0.25f * (0.25f * b0.v[e] + 0.75f * b1.v[e]);
             r1.v[e] = 0.75f * (0.75f * m1.v[e] + 0.25f * m2.v[e]) + 0.25f * (0.75f * b1.v[e] + 0.25f * b2.v[e]);
           }
-          emit(2 * j + 1, 2 * i, r0);
-          emit(2 * j + 1, 2 * i + 1, r1);
+          emit_sk(2 * j + 1, 2 * i, r0, k10);
+          emit_sk(2 * j + 1, 2 * i + 1, r1, k11);
         }
       } else {
 #pragma unroll
