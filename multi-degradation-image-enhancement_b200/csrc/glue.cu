@@ -142,14 +142,25 @@ __global__ void __launch_bounds__(256) up_add_input_kernel(const T* __restrict__
     const int im = max(i - 1, 0), ip = min(i + 1, IW - 1);
     float t[3][3][3];  // [row jm/j/jp][col im/i/ip][channel]
     const int rows[3] = {jm, j, jp}, cols[3] = {im, i, ip};
+    // all loads of the quad are requested before any arithmetic: nine 8-channel vectors of `a` (a_ld >= 8) and the
+    // two-pixel fp32 pairs of x for both output rows and the three channels
+    F8 av[3][3];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const T* p = an + (size_t(rows[r]) * IW + cols[c]) * a_ld;
+      for (int c = 0; c < 3; ++c) av[r][c] = load8<T>(an + (size_t(rows[r]) * IW + cols[c]) * a_ld);
+    float2 xv[2][3];
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) t[r][c][ch] = to_f32<T>(p[ch]);
-      }
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch)
+        xv[dy][ch] = *reinterpret_cast<const float2*>(xn + ch * plane + size_t(2 * j + dy) * OW + 2 * i);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) t[r][c][ch] = av[r][c].v[ch];
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
@@ -164,7 +175,7 @@ __global__ void __launch_bounds__(256) up_add_input_kernel(const T* __restrict__
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
           const float up = wy0 * (wx0 * t[r0][c0][ch] + wx1 * t[r0][c1][ch]) + wy1 * (wx0 * t[r1][c0][ch] + wx1 * t[r1][c1][ch]);
-          r.v[ch] = up + xn[ch * plane + size_t(oy) * OW + ox];
+          r.v[ch] = up + (dx ? xv[dy][ch].y : xv[dy][ch].x);
         }
         T* o = out + ((size_t(n) * OH + oy) * OW + ox) * out_ld;
         store8<T>(o, r);
