@@ -44,8 +44,8 @@ DENSE3X3 = {f"{blk}.layers.{l}": (c0 + 16 * l, div)
                                  ("decoder.final_dense", 3, 1)) for l in range(4)}
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per 32 x 1080p step from the `ncu --set full` capture
 # summarised in profiles/r01_allconv_ncu.md: the 16 dense-block 3x3 launches, and all 29 convolution launches.
-DENSE3X3_NCU_TRAFFIC_BYTES = 52036029000
-ALLCONV_NCU_TRAFFIC_BYTES = 89808781000
+DENSE3X3_NCU_TRAFFIC_BYTES = 52039405000
+ALLCONV_NCU_TRAFFIC_BYTES = 89809026000
 
 
 def measured_peaks():
