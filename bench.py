@@ -135,7 +135,7 @@ def cpu_oracle_rate(h, w, budget_s, threads):
     return rows * w / 1e6 / dt, f"1 x 3 x {rows} x {w} fp32 image (rows sized to ~{budget_s:.0f} s), torch CPU oracle port", dt
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """Reference arm: the reference's algorithm on host cores (oracle port), bounded sample per step."""
     if rank != 0:
         return
@@ -167,7 +167,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -189,9 +189,20 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # Rank 0 prints ONE JSON line on stdout.  Libraries write banners there from native code (e.g. "NCCL version ..." at
+    # process-group creation), so file descriptor 1 points at stderr until the line is printed.
+    sys.stdout.flush()
+    _stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(_stdout_fd, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     if not torch.cuda.is_available():
@@ -201,8 +212,6 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     from models.cdan import CDAN
@@ -319,7 +328,7 @@ def main():
             threads = os.cpu_count() or 1
             mp_s, sample, _ = cpu_oracle_rate(h, w, args.cpu_budget, threads)
             line["cpu_baseline"] = {"value": mp_s, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
