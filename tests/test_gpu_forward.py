@@ -177,6 +177,26 @@ def test_host_buffer_pipeline_ramped_schedule(cuda_device):
     plan.set_option("host_chunk", 8)
 
 
+def test_multi_degradation_routing_on_device(cuda_device):
+    """SURVEY 8 f-3 (config C4): a mixed batch is bucketed per flagged degradation and each bucket runs through that
+    degradation's CDAN weights on the native plan; multi-label images are enhanced in class order, unlabelled ones are
+    untouched.  The forward is batch-independent, so routing must equal enhancing every image on its own, bitwise."""
+    from routing import DegradationRouter
+    nets = {"noise": make_net(stress_state_dict(1), "bf16", cuda_device), "blur": make_net(stress_state_dict(2), "bf16", cuda_device)}
+    router = DegradationRouter(nets, class_order=["noise", "blur"], thresholds=[0.5, 0.4])
+    x = ramp_input(5, 16, 24, seed=8).to(cuda_device)
+    probs = torch.tensor([[0.9, 0.1], [0.2, 0.45], [0.6, 0.9], [0.1, 0.1], [0.5, 0.39]], device=cuda_device)
+    with torch.no_grad():
+        y = router(x, probs)
+        want = x.clone()
+        for i, classes in enumerate([["noise"], ["blur"], ["noise", "blur"], [], ["noise"]]):
+            for c in classes:
+                want[i:i + 1] = nets[c](want[i:i + 1].contiguous())
+    assert router.last_bucket_sizes == {"noise": 3, "blur": 2}
+    assert torch.equal(y, want)
+    assert torch.equal(y[3], x[3])
+
+
 _LAYOUT_AB = """
 import sys, hashlib, torch
 sys.path.insert(0, {pkg!r}); sys.path.insert(0, {root!r})
