@@ -103,6 +103,12 @@ CDAN_API int cdan_postprocess(void* stream, int op, float arg, const float* x, f
  * after `permute(1,2,0)`): x fp32 [N,3,H,W] (device) -> y uint8 [N,H,W,3] (device), truncation toward zero.  H*W % 4 == 0.
  * Stream-ordered; a quarter of the bytes of x then cross PCIe. */
 CDAN_API int cdan_quantize_u8(void* stream, const float* x, unsigned char* y, int N, int H, int W);
+/* Input side (reference data/dataset.py:86-92 with utils/transforms_factory.py:50-86: `A.Resize` = cv2.resize INTER_LINEAR
+ * on the uint8 image, `A.Normalize(mean 0, std 1, max_pixel_value 255)`, `ToTensorV2`): src uint8 [N,Hs,Ws,3] (device) ->
+ * dst fp32 [N,3,Hd,Wd] (device).  Bit-exact with cv2.resize for 8-bit images (OpenCV's 11-bit fixed-point bilinear);
+ * the normalisation multiplies by float32(1/255).  Synchronises the stream. */
+CDAN_API int cdan_resize_normalize_u8(void* stream, const unsigned char* src, int N, int Hs, int Ws, float* dst, int Hd,
+                                      int Wd);
 /* PSNR and SSIM with torchmetrics' default settings (reference utils/metrics_factory.py:74-94); result_host[0] =
  * PSNR (dB), result_host[1] = SSIM.  Synchronises the stream. */
 CDAN_API int cdan_psnr_ssim(void* stream, const float* pred, const float* target, int N, int C, int H, int W,

@@ -42,6 +42,7 @@ _PROTOTYPES = {
                                       _c_void_p]),
     "cdan_postprocess": (_c_int, [_c_void_p, _c_int, _c_float, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
     "cdan_quantize_u8": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
+    "cdan_resize_normalize_u8": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_int, _c_int]),
     "cdan_psnr_ssim": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
                                 ctypes.POINTER(_c_float)]),
 }
@@ -250,6 +251,22 @@ def quantize_u8(images: torch.Tensor) -> torch.Tensor:
     y = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _check(lib().cdan_quantize_u8(_c_void_p(_stream(dev)), _ptr(x), _ptr(y), n, h, w), "quantize_u8")
+    return y
+
+
+def resize_normalize_u8(images_u8: torch.Tensor, out_hw) -> torch.Tensor:
+    """[N,Hs,Ws,3] uint8 (CUDA) -> [N,3,Hd,Wd] float32 (CUDA): the reference's input transform `A.Resize(Hd, Wd)`
+    (cv2.resize INTER_LINEAR on the uint8 image, bit-exact) + `A.Normalize(0, 1, 255)` + `ToTensorV2`
+    (utils/transforms_factory.py:50-86), on the device — the uint8 source is a quarter of the bytes over PCIe."""
+    if images_u8.dtype != torch.uint8 or images_u8.dim() != 4 or images_u8.shape[3] != 3 or not images_u8.is_cuda:
+        raise RuntimeError("cdan_b200: resize_normalize_u8 expects a CUDA uint8 tensor [N,H,W,3]")
+    x = images_u8.contiguous()
+    n, hs, ws, _ = x.shape
+    hd, wd = int(out_hw[0]), int(out_hw[1])
+    y = torch.empty((n, 3, hd, wd), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(lib().cdan_resize_normalize_u8(_c_void_p(_stream(x.device)), _ptr(x), n, hs, ws, _ptr(y), hd, wd),
+               "resize_normalize_u8")
     return y
 
 

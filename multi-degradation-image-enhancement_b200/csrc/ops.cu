@@ -164,6 +164,46 @@ int cdan_postprocess(void* stream, int op, float arg, const float* x, float* y, 
   return 0;
 }
 
+namespace {
+// Source indices and 11-bit weights of cv::resize INTER_LINEAR for one axis (resize.cpp, resizeGeneric_ set-up): the
+// coordinate is evaluated in double, its fraction in float; horizontally the fraction is forced to 0 where the two-tap
+// window leaves the image, vertically only the two row indices are clipped.  Layout: [i0 | i1 | w0 | w1], n entries each.
+std::vector<int> cv_linear_table(int src, int dst, bool vertical) {
+  std::vector<int> t(size_t(4) * dst);
+  const double scale = 1.0 / (double(dst) / double(src));
+  for (int d = 0; d < dst; ++d) {
+    float f = float((d + 0.5) * scale - 0.5);
+    int s = int(floorf(f));
+    f -= float(s);
+    if (!vertical) {
+      if (s < 0) { f = 0.f; s = 0; }
+      if (s >= src - 1) { f = 0.f; s = src - 1; }
+    }
+    t[d] = std::min(std::max(s, 0), src - 1);
+    t[dst + d] = std::min(std::max(s + 1, 0), src - 1);
+    t[2 * dst + d] = int(lrintf((1.f - f) * 2048.f));  // saturate_cast<short>(float): round half to even
+    t[3 * dst + d] = int(lrintf(f * 2048.f));
+  }
+  return t;
+}
+}  // namespace
+
+int cdan_resize_normalize_u8(void* stream, const unsigned char* src, int N, int Hs, int Ws, float* dst, int Hd, int Wd) {
+  if (!src || !dst) return fail("cdan_resize_normalize_u8: NULL argument");
+  if (N <= 0 || Hs <= 0 || Ws <= 0 || Hd <= 0 || Wd <= 0) return fail("cdan_resize_normalize_u8: empty input or output");
+  cudaStream_t s = (cudaStream_t)stream;
+  const std::vector<int> xt = cv_linear_table(Ws, Wd, false), yt = cv_linear_table(Hs, Hd, true);
+  Scratch sc;
+  int *d_xt, *d_yt;
+  CDAN_TRY(sc.alloc((void**)&d_xt, xt.size() * sizeof(int)));
+  CDAN_TRY(sc.alloc((void**)&d_yt, yt.size() * sizeof(int)));
+  CDAN_CUDA_OK(cudaMemcpyAsync(d_xt, xt.data(), xt.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  CDAN_CUDA_OK(cudaMemcpyAsync(d_yt, yt.data(), yt.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  CDAN_TRY(resize_normalize_u8_launch(src, N, Hs, Ws, dst, Hd, Wd, d_xt, d_yt, s));
+  CDAN_CUDA_OK(cudaStreamSynchronize(s));  // the tables are freed on return
+  return 0;
+}
+
 int cdan_quantize_u8(void* stream, const float* x, unsigned char* y, int N, int H, int W) {
   if (!x || !y) return fail("cdan_quantize_u8: NULL argument");
   if (N <= 0 || H <= 0 || W <= 0) return fail("cdan_quantize_u8: empty input");

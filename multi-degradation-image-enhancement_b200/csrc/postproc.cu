@@ -305,6 +305,39 @@ int quantize_u8_launch(const float* x, uint8_t* y, int N, int H, int W, cudaStre
   return 0;
 }
 
+// Input side (reference data/dataset.py:86-92 + utils/transforms_factory.py:50-86): uint8 HWC images ->
+// cv2.resize(INTER_LINEAR) -> Normalize(mean 0, std 1, max 255) -> CHW float32.  The arithmetic is OpenCV's fixed-point
+// bilinear for 8-bit images (11-bit weights; resize.cpp HResizeLinear / VResizeLinear), restated and pinned bit-exactly
+// against cv2 in oracle/input_oracle.py; the per-column / per-row source indices and weights are computed on the host
+// with the same float/double operations OpenCV uses and arrive as tables [x0 | x1 | a0 | a1] and [y0 | y1 | b0 | b1].
+__global__ void __launch_bounds__(256) resize_normalize_u8_kernel(const uint8_t* __restrict__ src, int Hs, int Ws,
+                                                                   float* __restrict__ dst, int Hd, int Wd,
+                                                                   const int* __restrict__ xt, const int* __restrict__ yt) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, n = blockIdx.z;
+  if (x >= Wd) return;
+  const int x0 = xt[x], x1 = xt[Wd + x], a0 = xt[2 * Wd + x], a1 = xt[3 * Wd + x];
+  const int y0 = yt[y], y1 = yt[Hd + y], b0 = yt[2 * Hd + y], b1 = yt[3 * Hd + y];
+  const uint8_t* im = src + size_t(n) * Hs * Ws * 3;
+  const uint8_t *r0 = im + size_t(y0) * Ws * 3, *r1 = im + size_t(y1) * Ws * 3;
+  const float inv255 = 1.0f / 255.0f;  // float32 reciprocal, as albumentations.Normalize multiplies by it
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int h0 = int(r0[x0 * 3 + c]) * a0 + int(r0[x1 * 3 + c]) * a1;  // horizontal pass, scaled by 2^11
+    const int h1 = int(r1[x0 * 3 + c]) * a0 + int(r1[x1 * 3 + c]) * a1;
+    int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    v = min(max(v, 0), 255);
+    dst[((size_t(n) * 3 + c) * Hd + y) * Wd + x] = float(v) * inv255;
+  }
+}
+
+int resize_normalize_u8_launch(const uint8_t* src, int N, int Hs, int Ws, float* dst, int Hd, int Wd, const int* xt,
+                               const int* yt, cudaStream_t s) {
+  if (N > 65535 || Hd > 65535) return fail("resize_normalize_u8: batch or output height too large for one launch");
+  resize_normalize_u8_kernel<<<dim3((Wd + 255) / 256, Hd, N), 256, 0, s>>>(src, Hs, Ws, dst, Hd, Wd, xt, yt);
+  CDAN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int psnr_ssim_launch(const float* pred, const float* target, int N, int C, int H, int W, float* scratch, float* result,
                      cudaStream_t s) {
   const int planes = N * C;

@@ -157,6 +157,21 @@ def test_quantize_u8_bit_exact(cuda_device):
     assert np.array_equal(native.quantize_u8(big.to(cuda_device)).cpu().numpy(), O.quantize_u8(big))
 
 
+def test_resize_normalize_u8_bit_exact(cuda_device):
+    """cdan_resize_normalize_u8 against oracle/input_oracle.py (itself pinned bit-exactly to cv2.resize INTER_LINEAR):
+    integer bilinear -> the float32 outputs must be equal bit for bit.  Down- and up-scaling, odd sizes, batch > 1."""
+    import cdan_b200_native as native
+    from oracle.input_oracle import network_input
+    rng = np.random.default_rng(23)
+    for (hs, ws), (hd, wd), n in [((301, 517), (256, 384), 2), ((37, 53), (256, 384), 1), ((1080, 1920), (256, 384), 1),
+                                  ((8, 8), (24, 40), 3), ((256, 384), (256, 384), 1)]:
+        img = rng.integers(0, 256, (n, hs, ws, 3), dtype=np.uint8)
+        got = native.resize_normalize_u8(torch.from_numpy(img).to(cuda_device), (hd, wd)).cpu().numpy()
+        want = np.stack([network_input(img[i], (hd, wd)) for i in range(n)])
+        assert got.shape == (n, 3, hd, wd) and got.dtype == np.float32
+        assert np.array_equal(got, want), ((hs, ws), (hd, wd))
+
+
 def test_psnr_ssim_match_oracle(cuda_device):
     import cdan_b200_native as native
     g = torch.Generator().manual_seed(9)
