@@ -7,7 +7,7 @@
 // dimension: input row j is multiplied once by [W(r=2) | W(r=1) | W(r=0)] (N = 3*NT) and the three NT-column blocks
 // accumulate straight into the accumulators of output rows j-1, j, j+1, which sit in consecutive slots of a TMEM
 // RING.  The three horizontal taps are three A descriptors shifted by one pixel row (128 B) of the same stage.
-//   * N = 48 instead of 16 costs 44 instead of 39 cycles per tcgen05.mma (measured, profiles/r02_probe.log), so a
+//   * N = 48 instead of 16 costs 44 instead of 39 cycles per tcgen05.mma (measured, profiles/r01_mma_tmem_probe.log), so a
 //     16-channel dense layer issues 3x fewer, equally expensive MMAs: 20 % -> 55 % of the tensor pipe.
 //   * every activation row is loaded from HBM exactly once per strip (no vertical halo re-reads), stages are small
 //     (16 KB) so 8-12 of them are in flight per SM.
@@ -19,9 +19,17 @@
 // two ring slots of the same thread, horizontal pair = lane^1).
 // 1x1 convolutions use the same pipeline with a window of one slot and fresh accumulators (no clearing).
 //
-// Warp roles: 0 TMA producer (+ resident weights), 1 MMA issuer, 2 TMEM allocator, 4-11 epilogue (two groups of four,
-// alternating accumulator rows), 12-19 A-stage workers (dense pre-activation relu(s*x+t) in place, or the conv1 row
-// builder).  All waits are bounded (ptx::mbar_wait traps), so a protocol bug fails loudly instead of hanging.
+// Two kernels share this formulation:
+//   conv_stream_kernel<IN,FOLD,EPI>   one image row per stage: conv1 (planar fp32 input, K-fold, fused 2x2 max-pool),
+//                                     the TMA-fed layers (conv2 and decoder.conv3 in the WIDE nine-tap form with the
+//                                     weights resident, decoder.conv4 as a nine-tap fold) and the A/B variants of the
+//                                     dense layers.  Warp roles: 0 TMA producer (+ resident weights), 1 MMA issuer,
+//                                     2 TMEM allocator, 4-11 epilogue (two groups), then the A-stage workers.
+//   conv_stream2_kernel<FOLD,EPI,GP>  two image rows per stage: all dense-block layers (3x3 row fold, 1x1 transitions).
+//                                     GP selects the input layout (0 NHWC, 1 group-planar, 2 hybrid: compact NHWC head
+//                                     + 16-channel group planes); up to three MMA issuer warps take row
+//                                     pairs round-robin under a completion token.
+// All waits are bounded (ptx::mbar_wait traps), so a protocol bug fails loudly instead of hanging.
 #include <cuda.h>
 
 #include <algorithm>
