@@ -4,8 +4,9 @@ One rank owns a band of image rows (band boundaries at multiples of 8, so the th
 boundary) and runs the whole network on it.  Everything that looks across the boundary is an explicit exchange:
 
 * every 3x3 convolution / 3x3 transposed convolution : 1 halo row of its INPUT at that layer's resolution; at the image
-  border the halo is zero (the convolution's own padding; for dense layers it is applied AFTER the pre-activation,
-  reference models/cdan.py:41-46, so the activated rows are what travels);
+  border the halo is zero (the convolution's own padding).  Inside a dense block every feature map travels once, RAW:
+  the block input, then the 16 new channels of layers 0-2; each layer's pre-activation is applied to the received rows
+  locally and the out-of-image rows are zeroed after it (the reference pads after the activation, models/cdan.py:41-46);
 * every bilinear x2 upsampling (align_corners=False, models/cdan.py:137,145,153): 1 halo row of its input, at the image
   border the edge row is replicated (index clamping);
 * every SpatialGate 7x7 convolution (models/cbam.py:72-82): 3 halo rows of the 2-channel pooled map, zero at the border;
@@ -59,6 +60,16 @@ class TileComm:
         bot = bot_recv if bot_recv is not None else edge(x[:, :, rows - 1:].expand(n, c, h, w).contiguous())
         return torch.cat([top, x, bot], dim=2)
 
+    def zero_border_rows(self, x_ext: torch.Tensor, h: int) -> torch.Tensor:
+        """Zero the h halo rows that lie outside the image (first / last band only): padding applied AFTER an activation."""
+        if self.rank == 0 or self.rank == self.world - 1:
+            x_ext = x_ext.clone()
+            if self.rank == 0:
+                x_ext[:, :, :h] = 0
+            if self.rank == self.world - 1:
+                x_ext[:, :, x_ext.shape[2] - h:] = 0
+        return x_ext
+
     def allreduce(self, t: torch.Tensor, op: str) -> torch.Tensor:
         if self.world > 1:
             t = t.clone()
@@ -93,11 +104,17 @@ def _conv_block(comm, sd, prefix, x):
 
 
 def _dense_block(comm, sd, prefix, x, num_layers=4):
-    feats = [x]
+    """Every feature map of the concat travels ONCE, raw: the block input when the block starts, each layer's 16 new
+    channels when they are produced (the last layer's only feed the 1x1 transition and do not travel).  The receiving
+    band applies each layer's own pre-activation to the halo rows itself and zeroes the rows outside the image after it
+    (the reference pads after the activation, models/cdan.py:41-46)."""
+    ext = [comm.halo(x, 1, "zero")]  # feature maps with their halo rows
     for l in range(num_layers):
-        a = F.relu(_bn(sd, f"{prefix}.layers.{l}.0", torch.cat(feats, dim=1)))  # activate, THEN pad / exchange
-        feats.append(_conv3x3(comm, a, sd[f"{prefix}.layers.{l}.2.weight"], sd[f"{prefix}.layers.{l}.2.bias"]))
-    a = F.relu(_bn(sd, f"{prefix}.transition_layer.0", torch.cat(feats, dim=1)))
+        a = F.relu(_bn(sd, f"{prefix}.layers.{l}.0", torch.cat(ext, dim=1)))
+        a = comm.zero_border_rows(a, 1)
+        y = F.conv2d(a, sd[f"{prefix}.layers.{l}.2.weight"], sd[f"{prefix}.layers.{l}.2.bias"], padding=(0, 1))
+        ext.append(comm.halo(y, 1, "zero") if l + 1 < num_layers else F.pad(y, (0, 0, 1, 1)))
+    a = F.relu(_bn(sd, f"{prefix}.transition_layer.0", torch.cat([e[:, :, 1:-1] for e in ext], dim=1)))
     return F.conv2d(a, sd[f"{prefix}.transition_layer.2.weight"], sd[f"{prefix}.transition_layer.2.bias"])
 
 

@@ -16,6 +16,11 @@ def test_band_rows_follow_the_survey_split():
     sizes = [b - a for a, b in bands]
     assert bands[0][0] == 0 and bands[-1][1] == 2160 and all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
     assert sorted(sizes) == [264, 264] + [272] * 6 and all(s % 8 == 0 for s in sizes)
+    import spatial_tiling
+    assert spatial_tiling.band_rows(2160, 8) == bands  # the product-side plan and the oracle agree
+    # C5: an interior band of the 4K image receives ~7 MB per forward in bf16, every message <= 0.5 MB
+    assert max(e.rows * e.channels * (3840 // e.div) * 2 for e in spatial_tiling.halo_schedule()) == 512 * 480 * 2
+    assert 6.5e6 < spatial_tiling.halo_bytes_received(1, 3840, rank=3, world=8) < 7.5e6
     with pytest.raises(ValueError):
         band_rows(36, 2)
     with pytest.raises(ValueError):
@@ -63,3 +68,7 @@ def test_row_tiled_forward_matches_untiled(tmp_path, world):
     # 20 3x3 convolutions (4 ConvBlocks + 16 dense layers; the 1x1 transitions need none) + 4 transposed + 3 bilinear
     # + 4 SpatialGate 7x7 = 31 halo exchanges; 4 ChannelGates x (SUM, MAX) = 8 all-reduces
     assert r["stats"]["halo_exchanges"] == 31 and r["stats"]["allreduces"] == 8
+    # the product-side plan (spatial_tiling.halo_schedule) predicts exactly what the executable schedule moved
+    from spatial_tiling import CHANNEL_GATE_ALLREDUCES, halo_bytes_received, halo_schedule
+    assert len(halo_schedule()) == 31 and 2 * len(CHANNEL_GATE_ALLREDUCES) == 8
+    assert r["stats"]["halo_bytes"] == halo_bytes_received(batch=2, width=40, rank=0, world=world, elem_size=8)
