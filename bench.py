@@ -1,19 +1,24 @@
 #!/usr/bin/env python
 """bench.py — CDAN forward throughput on B200 (the metric of BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--height H] [--width W]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c3|c2] [--scaling weak|strong]
 
-A "step" is one eval-mode CDAN forward over one synthetic batch.  Workload at every N: 32 x 3 x 1080 x 1920 images
-PER GPU (BASELINE config C3's batch, the configuration the metric is quoted on; batch-sharded, no collective ->
-weak scaling).  `value` = megapixels/s with inputs resident in HBM, device-timed (CUDA events, max over ranks);
-`e2e` = the same through the host-buffer C-ABI call (pinned host input -> H2D -> forward -> D2H) per step.
-`roofline` is for the tcgen05 convolutions (conv_stream_kernel + conv_umma_kernel, all conv launches of one step) against
-the measured bf16 peak; `roofline_dense` is for the single heaviest kernel, conv_stream2_kernel<4,0,GP> (the 16 dense-block
-3x3 layers, ~33 % of the step), against the measured HBM bandwidth; `cpu_baseline` is the CPU oracle port timed on this
-box's host cores on a bounded sample.
-Inputs (796 MB per step) and activations are far larger than the 126 MB L2, so no explicit L2 flush is needed.
-`--impl reference` times the reference algorithm's CPU restatement (oracle/, the reference itself is a Python tree that
-does not travel to the GPU box) on all host threads.
+A "step" is one eval-mode CDAN forward over one synthetic batch.
+  --config c3 (default): BASELINE config 3, the configuration the metric is quoted on: 32 x 3 x 1080 x 1920 images.
+      --scaling weak (default): 32 images PER GPU at every N (batch-sharded, no collective).
+      --scaling strong: SURVEY 8(e)'s split of C3: 32 images in total, 32/16/8/4 per GPU.
+  --config c2: BASELINE config 2, 64 x 3 x 256 x 256 on one GPU (per GPU when N > 1).
+`value` = megapixels/s with inputs resident in HBM, device-timed (CUDA events, max over ranks).
+`e2e` = the same through the host-buffer C-ABI call cdan_forward_host (pinned fp32 NCHW host input -> H2D -> forward ->
+D2H fp32 NCHW, the reference's tensor contract at the module boundary); `e2e_u8` = the reference's image data path
+(uint8 HWC -> /255 -> forward -> x255 -> uint8 HWC) through cdan_forward_host_u8, a quarter of the PCIe bytes.
+`roofline` is for the tcgen05 convolutions (all conv launches of one step) against the measured sustained bf16 peak;
+`roofline_dense` for the dense-block kernels against the measured HBM bandwidth; `roofline_cbam` for the CBAM group.
+`cpu_baseline` (N = 1 only, computed before any process group exists) and `--impl reference` time the reference's own
+CPU forward (oracle/_ref = the unmodified /root/reference files vendored at build time; the oracle port only when that
+directory is missing) on this box's host cores on a bounded sample.
+Inputs and activations are far larger than the 126 MB L2 at C3; at C2 a 256 MB scratch buffer is written between
+timed forwards to flush L2 (stated in `config.l2`).
 """
 from __future__ import annotations
 
@@ -46,6 +51,7 @@ DENSE3X3 = {f"{blk}.layers.{l}": (c0 + 16 * l, div)
 # summarised in profiles/r01_allconv_ncu.md: the 16 dense-block 3x3 launches, and all 29 convolution launches.
 DENSE3X3_NCU_TRAFFIC_BYTES = 52039405000
 ALLCONV_NCU_TRAFFIC_BYTES = 89809026000
+CBAM_NCU_TRAFFIC_BYTES = None  # filled from profiles/r02_* once captured
 
 
 def measured_peaks():
@@ -114,60 +120,83 @@ def synthetic_batch(n, h, w, seed=42):
     return torch.rand((n, 3, h, w), generator=g)
 
 
-def cpu_oracle_rate(h, w, budget_s, threads):
-    """MP/s of the CPU oracle port on a bounded sample: one image, as many rows (multiple of 8) as fit the budget."""
-    from oracle.cdan_oracle import cdan_forward
-    from oracle.stress_init import default_state_dict
+def default_weights(seed=42):
+    """`torch.manual_seed(42); CDAN()` — PyTorch's default initialisation of the module tree."""
+    from models.cdan import CDAN
+    torch.manual_seed(seed)
+    net = CDAN()
+    return {k: v.detach().clone() for k, v in net.state_dict().items()}
+
+
+def reference_weights(seed=42):
+    """Same seeded default init drawn through the REFERENCE's own module (oracle/_ref) when present, so that the reference
+    arm imports none of this repository's model code; bit-identical to default_weights (same registration order)."""
+    from oracle.build_ref import load_ref, ref_available
+    if not ref_available():
+        return default_weights(seed)
+    cdan_mod, _, _ = load_ref()
+    torch.manual_seed(seed)
+    net = cdan_mod.CDAN()
+    return {k: v.detach().clone() for k, v in net.state_dict().items()}
+
+
+def cpu_reference_rate(sd, h, w, budget_s, threads):
+    """MP/s of the reference's CPU forward on a bounded sample: one image, as many rows (multiple of 8) as fit the
+    budget.  Returns (MP/s, sample description, seconds, kind) with kind = "reference" (oracle/_ref) or "port"."""
+    from oracle.build_ref import reference_forward_fn
     torch.set_num_threads(threads)
-    sd = default_state_dict(42)
+    fwd, kind = reference_forward_fn(sd)
     probe = synthetic_batch(1, 64, min(w, 256), seed=1)
-    with torch.no_grad():
-        cdan_forward(sd, probe)  # warm-up (thread pools, allocator)
-        t0 = time.perf_counter()
-        cdan_forward(sd, probe)
-        rate = probe.shape[2] * probe.shape[3] / (time.perf_counter() - t0)  # px/s, pessimistic for larger images
+    fwd(probe)  # warm-up (thread pools, allocator)
+    t0 = time.perf_counter()
+    fwd(probe)
+    rate = probe.shape[2] * probe.shape[3] / (time.perf_counter() - t0)  # px/s, pessimistic for larger images
     rows = int(max(8, min(h, (budget_s * rate / w) // 8 * 8)))
     x = synthetic_batch(1, rows, w, seed=42)
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        cdan_forward(sd, x)
-        dt = time.perf_counter() - t0
-    return rows * w / 1e6 / dt, f"1 x 3 x {rows} x {w} fp32 image (rows sized to ~{budget_s:.0f} s), torch CPU oracle port", dt
+    t0 = time.perf_counter()
+    fwd(x)
+    dt = time.perf_counter() - t0
+    what = "unmodified reference models/cdan.py (oracle/_ref)" if kind == "reference" else "torch CPU oracle port"
+    return rows * w / 1e6 / dt, f"1 x 3 x {rows} x {w} fp32 image (rows sized to ~{budget_s:.0f} s), {what}", dt, kind
 
 
 def run_reference(args, rank, world, emit):
-    """Reference arm: the reference's algorithm on host cores (oracle port), bounded sample per step."""
+    """Reference arm: the reference's own CPU forward on host cores, bounded sample per step; rank 0 only."""
     if rank != 0:
         return
+    from oracle.build_ref import reference_forward_fn
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    from oracle.cdan_oracle import cdan_forward
-    from oracle.stress_init import default_state_dict
-    sd = default_state_dict(42)
+    sd = reference_weights(42)
     total = args.steps + args.warmup
     budget = max(1.0, 150.0 / max(1, total))
-    mp_s, sample, _ = cpu_oracle_rate(args.height, args.width, budget, threads)
+    mp_s, sample, _, kind = cpu_reference_rate(sd, args.height, args.width, budget, threads)
     rows = int(sample.split(" x ")[2])
+    fwd, kind = reference_forward_fn(sd)
     x = synthetic_batch(1, rows, args.width, seed=42)
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            cdan_forward(sd, x)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            cdan_forward(sd, x)
-        dt = (time.perf_counter() - t0) / max(1, args.steps)
+    for _ in range(args.warmup):
+        fwd(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fwd(x)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
     value = rows * args.width / 1e6 / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CDAN forward {args.batch}x3x{args.height}x{args.width} per GPU (C3); reference arm "
-                               f"times a bounded sample per step", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(args, args.batch), "note": "reference arm times a bounded sample per step",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def workload_name(args, n):
+    tag = {"c3": "BASELINE C3", "c2": "BASELINE C2"}[args.config]
+    return f"CDAN forward {n}x3x{args.height}x{args.width} per GPU ({tag}), batch-sharded, no collective"
 
 
 def main():
@@ -176,15 +205,23 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="images per GPU")
-    ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--config", default="c3", choices=["c3", "c2"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the config's batch)")
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", action="store_true", help="print the per-launch timing table to stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg_batch, cfg_h, cfg_w = {"c3": (32, 1080, 1920), "c2": (64, 256, 256)}[args.config]
+    args.height = args.height or cfg_h
+    args.width = args.width or cfg_w
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.batch is None:
+        args.batch = max(1, cfg_batch // world_env) if args.scaling == "strong" else cfg_batch
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -207,27 +244,43 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA kernels are the product (no CPU fallback)")
+    n, h, w = args.batch, args.height, args.width
+
+    # ---- CPU baseline: rank 0, N = 1 only, BEFORE any process group / GPU work exists (at N > 1 the other ranks would
+    #      spin in a barrier on the same cores and the figure is meaningless; the N = 1 line carries it)
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        mp_s, sample, _, kind = cpu_reference_rate(default_weights(42), h, w, args.cpu_budget, threads)
+        cpu_baseline = {"value": mp_s, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
+
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    from host_affinity import bind_to_gpu_node
+    numa = bind_to_gpu_node(local_rank) if world > 1 else {"bound": False, "note": "single rank: not bound"}
+    torch.set_num_threads(max(1, min(8, len(os.sched_getaffinity(0)))))
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
     from models.cdan import CDAN
-    from oracle.stress_init import default_state_dict  # weights only (seeded init from the key schema)
 
-    n, h, w = args.batch, args.height, args.width
     net = CDAN().set_compute_dtype(args.dtype)
-    net.load_state_dict(default_state_dict(42))
+    net.load_state_dict(default_weights(42))
     net = net.to(dev).eval()
     sampler = ClockSampler(local_rank)  # started early: nvidia-smi needs a few hundred ms before its first sample
     sampler.start()
     x_host = synthetic_batch(n, h, w, seed=42 + rank).pin_memory()
     y_host = torch.empty_like(x_host).pin_memory()
+    xu_host = (x_host * 255.0).to(torch.uint8).permute(0, 2, 3, 1).contiguous().pin_memory()
+    yu_host = torch.empty_like(xu_host).pin_memory()
     x = x_host.to(dev)
     y = torch.empty_like(x)
     plan = net.native_plan(dev)
+    # L2 flush between timed forwards when the working set could stay resident (C2: 50 MB of input): write 256 MB
+    small = n * h * w * 3 * 4 < 512 * 2 ** 20
+    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev) if small else None
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -244,35 +297,49 @@ def main():
     # ---- timed region: K forwards, inputs resident in HBM; per-launch CUDA-event spans recorded alongside
     plan.set_option("profile", 1)
     plan.profile_read()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_region0 = time.perf_counter()
-    ev0.record()
-    for _ in range(args.steps):
-        plan.forward(x, out=y)
-    ev1.record()
-    barrier()
+    if flush is None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            plan.forward(x, out=y)
+        ev1.record()
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+    else:
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for e0, e1 in evs:
+            flush.fill_(1)  # untimed: evict the previous forward's tensors from L2
+            e0.record()
+            plan.forward(x, out=y)
+            e1.record()
+        barrier()
+        ms_total = sum(e0.elapsed_time(e1) for e0, e1 in evs)
     clocks = sampler.stop(t_region0, time.perf_counter(), t_warm0)
-    ms_total = ev0.elapsed_time(ev1)
     spans = plan.profile_read()
     plan.set_option("profile", 0)
     launches_per_step = plan.last_launch_count
 
-    # ---- end-to-end through the host-buffer entry point (H2D + forward + D2H inside the timed region)
-    e2e_steps = max(1, min(args.steps, 5))
-    plan.forward_host(x_host, y_host)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        plan.forward_host(x_host, y_host)
-    torch.cuda.synchronize(dev)
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    # ---- end-to-end through the host-buffer entry points (H2D + forward + D2H inside the timed region)
+    def time_host(fn, xin, yout):
+        steps = max(1, min(args.steps, 5))
+        fn(xin, yout)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn(xin, yout)
+        torch.cuda.synchronize(dev)
+        return (time.perf_counter() - t0) / steps
 
-    t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
+    e2e_s = time_host(plan.forward_host, x_host, y_host)
+    e2e_u8_s = time_host(plan.forward_host_u8, xu_host, yu_host)
+
+    t = torch.tensor([ms_total, e2e_s, e2e_u8_s], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t[0]) / args.steps
-    e2e_s = float(t[1])
+    e2e_s, e2e_u8_s = float(t[1]), float(t[2])
     mp_per_step_total = world * n * h * w / 1e6
 
     if rank == 0:
@@ -287,23 +354,31 @@ def main():
         if args.layers:
             for k, v in sorted(spans.items(), key=lambda kv: -kv[1][0]):
                 print(f"  {k:60s} {v[0] / args.steps:9.3f} ms/step  x{v[1] // args.steps}", file=sys.stderr)
+        c3_full = (n, h, w) == (32, 1080, 1920)
         line = {
             "metric": METRIC, "value": mp_per_step_total / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "images_per_s": world * n / (ms_step * 1e-3),
-            "config": {"workload": f"CDAN forward {n}x3x{h}x{w} per GPU (BASELINE C3 batch), batch-sharded, no collective",
-                       "batch_per_gpu": n, "height": h, "width": w, "weights": "seeded default-like init (random)",
-                       "l2": "inputs+activations >> 126 MB L2 (no flush needed)", "parallelism": f"dp{world}"},
+            "config": {"workload": workload_name(args, n), "name": args.config,
+                       "batch_per_gpu": n, "global_batch": n * world, "height": h, "width": w,
+                       "weights": "torch.manual_seed(42); CDAN() default init (random)",
+                       "l2": ("256 MB buffer written between timed forwards (L2 flush); per-forward CUDA events summed"
+                              if flush is not None else "inputs+activations >> 126 MB L2 (no flush needed)"),
+                       "parallelism": f"dp{world}", "host_numa": numa},
             "clocks": clocks,
             "e2e": {"value": mp_per_step_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * 3 * h * w * 4,
                     "d2h_bytes_per_step": n * 3 * h * w * 4, "ms_per_step": e2e_s * 1e3,
                     "api": "Plan.forward_host -> cdan_forward_host (pinned fp32 NCHW host buffers)"},
+            "e2e_u8": {"value": mp_per_step_total / e2e_u8_s, "unit": UNIT, "h2d_bytes_per_step": n * 3 * h * w,
+                       "d2h_bytes_per_step": n * 3 * h * w, "ms_per_step": e2e_u8_s * 1e3,
+                       "api": "Plan.forward_host_u8 -> cdan_forward_host_u8 (pinned uint8 NHWC host buffers; /255 and "
+                              "x255 quantisation on the device, the reference's image data path)"},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "tensor", "kernel": "tcgen05 convolutions: conv_stream2_kernel + conv_stream_kernel + conv_umma_kernel (all conv launches of a step)",
+            "roofline": {"bound": "tensor", "kernel": "tcgen05 convolutions: dense_fused_kernel + conv_stream2_kernel + conv_stream_kernel + conv_umma_kernel (all conv launches of a step)",
                          "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tensor"],
-                         "traffic": ALLCONV_NCU_TRAFFIC_BYTES if (n, h, w) == (32, 1080, 1920) else None,
+                         "traffic": ALLCONV_NCU_TRAFFIC_BYTES if c3_full else None,
                          "peak_source": peaks["source"] + " (sustained)",
                          "launches_per_step": conv_launches, "kernel_ms_per_step": conv_ms,
                          "kernel_share_of_step": conv_ms / ms_step if ms_step else None,
@@ -311,6 +386,7 @@ def main():
             "roofline_cbam": {"bound": "hbm", "achieved": cbam_bytes / (cbam_ms * 1e-3) / 1e9 if cbam_ms else 0.0,
                               "peak": peaks["hbm"], "unit": "GB/s",
                               "frac": (cbam_bytes / (cbam_ms * 1e-3) / 1e9 / peaks["hbm"]) if cbam_ms else 0.0,
+                              "traffic": CBAM_NCU_TRAFFIC_BYTES if c3_full else None,
                               "kernel_ms_per_step": cbam_ms, "note": "achieved = compulsory 144 B/px over the 4 CBAM sites"},
             "glue_ms_per_step": glue_ms,
         }
@@ -319,15 +395,13 @@ def main():
         if dense_ms > 0:
             gbs = dense_bytes / (dense_ms * 1e-3) / 1e9
             line["roofline_dense"] = {
-                "bound": "hbm", "kernel": "conv_stream2_kernel<4,0,GP> (16 dense-block 3x3 launches of a step; GP=1 group-planar final dense block, GP=2 hybrid buffers of dense blocks 1-3)",
+                "bound": "hbm", "kernel": "conv_stream2_kernel<4,0,GP> (dense-block 3x3 launches of a step that are not fused)",
                 "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-                "traffic": DENSE3X3_NCU_TRAFFIC_BYTES if (n, h, w) == (32, 1080, 1920) else None,
+                "traffic": DENSE3X3_NCU_TRAFFIC_BYTES if c3_full else None,
                 "algorithmic_bytes_per_step": dense_bytes, "kernel_ms_per_step": dense_ms,
-                "kernel_share_of_step": dense_ms / ms_step if ms_step else None, "launches_per_step": len(DENSE3X3)}
-        if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            mp_s, sample, _ = cpu_oracle_rate(h, w, args.cpu_budget, threads)
-            line["cpu_baseline"] = {"value": mp_s, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+                "kernel_share_of_step": dense_ms / ms_step if ms_step else None}
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
         emit(line)
     if dist is not None:
         dist.barrier()

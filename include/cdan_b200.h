@@ -65,6 +65,11 @@ CDAN_API int cdan_forward(cdan_plan* plan, void* stream, const float* x, float* 
  * the H2D copy of the next and the D2H copy of the previous sub-batch overlap the forward of the current one on
  * separate streams.  Returns after the last D2H copy has completed. */
 CDAN_API int cdan_forward_host(cdan_plan* plan, const float* x_host, float* y_host, int N, int H, int W);
+/* The reference's real data path end to end (uint8 image -> /255 -> forward -> x255 -> uint8; data/dataset.py:86-92 with
+ * `A.Normalize(0,1,255)` + `ToTensorV2`, models/model.py:80-83): x_host, y_host are interleaved uint8 [N,H,W,3] HOST buffers.
+ * Per sub-batch the uint8 pixels cross PCIe (a quarter of the fp32 bytes each way), are normalised on the device
+ * (x = u8 * float32(1/255)), run through cdan_forward and are quantised on the device exactly as cdan_quantize_u8. */
+CDAN_API int cdan_forward_host_u8(cdan_plan* plan, const unsigned char* x_host, unsigned char* y_host, int N, int H, int W);
 
 /* Read an intermediate tensor of the most recent cdan_forward as fp32 NCHW (per-stage parity tests).
  * Names: "enc.out1","enc.out2","enc.out3" (max-pooled ConvBlock outputs = skip connections), "enc.dense1".."enc.dense3",

@@ -31,6 +31,7 @@ _PROTOTYPES = {
     "cdan_workspace_bytes": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, ctypes.POINTER(ctypes.c_size_t)]),
     "cdan_forward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
     "cdan_forward_host": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
+    "cdan_forward_host_u8": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
     "cdan_stage_read": (_c_int, [_c_void_p, _c_void_p, _c_char_p, _c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "cdan_last_launch_count": (_c_int, [_c_void_p]),
     "cdan_profile_read": (_c_int, [_c_void_p, ctypes.c_char_p, ctypes.c_size_t]),
@@ -157,6 +158,16 @@ class Plan:
         y = out_host if out_host is not None else torch.empty_like(x_host)
         n, _, h, w = x_host.shape
         _check(lib().cdan_forward_host(self._h, _ptr(x_host), _ptr(y), n, h, w), "forward_host")
+        return y
+
+    def forward_host_u8(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """uint8 [N,H,W,3] host buffers in/out: the reference's image data path (uint8 -> /255 -> forward -> x255 ->
+        uint8) with normalisation and quantisation on the device; a quarter of the PCIe bytes of forward_host."""
+        if x_host.is_cuda or x_host.dtype != torch.uint8 or not x_host.is_contiguous() or x_host.dim() != 4 or x_host.shape[3] != 3:
+            raise RuntimeError("cdan_b200: forward_host_u8 needs a contiguous uint8 CPU tensor [N,H,W,3]")
+        y = out_host if out_host is not None else torch.empty_like(x_host)
+        n, h, w, _ = x_host.shape
+        _check(lib().cdan_forward_host_u8(self._h, _ptr(x_host), _ptr(y), n, h, w), "forward_host_u8")
         return y
 
     def stage(self, name: str) -> torch.Tensor:

@@ -54,6 +54,7 @@ size_t metrics_scratch_floats(int N, int H, int W);
 // result[0] = PSNR, result[1] = SSIM (device pointer, 2 floats)
 int resize_normalize_u8_launch(const uint8_t* src, int N, int Hs, int Ws, float* dst, int Hd, int Wd, const int* xt,
                                const int* yt, cudaStream_t s);
+int normalize_u8_launch(const uint8_t* src, float* dst, int N, int H, int W, cudaStream_t s);
 int quantize_u8_launch(const float* x, uint8_t* y, int N, int H, int W, cudaStream_t s);
 int psnr_ssim_launch(const float* pred, const float* target, int N, int C, int H, int W, float* scratch, float* result,
                      cudaStream_t s);

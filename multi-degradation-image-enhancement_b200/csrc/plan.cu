@@ -585,8 +585,8 @@ int cdan_forward(cdan_plan* p, void* stream, const float* x, float* y, int N, in
   return forward_impl(p, (cudaStream_t)stream, x, y, N, H, W);
 }
 
-int cdan_forward_host(cdan_plan* p, const float* x_host, float* y_host, int N, int H, int W) {
-  if (!p || !x_host || !y_host) return fail("cdan_forward_host: NULL argument");
+// Host-buffer pipeline shared by cdan_forward_host (fp32 NCHW buffers) and cdan_forward_host_u8 (uint8 NHWC buffers).
+static int forward_host_impl(cdan_plan* p, const void* x_host, void* y_host, int N, int H, int W, bool u8) {
   DeviceGuard g(p->device);
   if (H % 8 || W % 8 || N <= 0) return fail("cdan_forward_host: H and W must be multiples of 8");
   // Sub-batch pipeline over three streams: the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the forward
@@ -603,13 +603,15 @@ int cdan_forward_host(cdan_plan* p, const float* x_host, float* y_host, int N, i
   }
   const int cb = std::max(1, std::min(N, p->host_chunk));
   const size_t img_floats = size_t(3) * H * W, slot_floats = size_t(cb) * img_floats;
-  if (p->host_stage_bytes < 4 * slot_floats * sizeof(float)) {
+  // device staging per slot: fp32 x | fp32 y | (u8 path) u8 x | u8 y
+  const size_t slot_bytes = 2 * slot_floats * sizeof(float) + (u8 ? 2 * align_up(slot_floats, 256) : 0);
+  if (p->host_stage_bytes < 2 * slot_bytes) {
     CDAN_CUDA_OK(cudaDeviceSynchronize());
     if (p->host_stage) CDAN_CUDA_OK(cudaFree(p->host_stage));
     p->host_stage = nullptr;
     p->host_stage_bytes = 0;
-    CDAN_CUDA_OK(cudaMalloc(&p->host_stage, 4 * slot_floats * sizeof(float)));
-    p->host_stage_bytes = 4 * slot_floats * sizeof(float);
+    CDAN_CUDA_OK(cudaMalloc(&p->host_stage, 2 * slot_bytes));
+    p->host_stage_bytes = 2 * slot_bytes;
   }
   CDAN_TRY(ensure_workspace(p, cb, H, W));
   // Chunk schedule: full chunks of `cb` images in the middle (large sub-batches run the kernels at their best rate), a
@@ -632,25 +634,43 @@ int cdan_forward_host(cdan_plan* p, const float* x_host, float* y_host, int N, i
       for (int rest = N; rest > 0; rest -= cb) sched.push_back(std::min(cb, rest));
     }
   }
+  const size_t img_host_bytes = u8 ? img_floats : img_floats * sizeof(float);
   int k = 0, n0 = 0;
   for (size_t ci = 0; ci < sched.size(); n0 += sched[ci], ++ci, ++k) {
     const int nb = sched[ci], slot = k & 1;
-    float* xs = p->host_stage + size_t(slot) * 2 * slot_floats;
+    char* base = reinterpret_cast<char*>(p->host_stage) + size_t(slot) * slot_bytes;
+    float* xs = reinterpret_cast<float*>(base);
     float* ys = xs + slot_floats;
-    const size_t bytes = size_t(nb) * img_floats * sizeof(float);
+    uint8_t* xu = reinterpret_cast<uint8_t*>(ys + slot_floats);
+    uint8_t* yu = xu + align_up(slot_floats, 256);
+    const size_t bytes = size_t(nb) * img_host_bytes;
     if (k >= 2) CDAN_CUDA_OK(cudaStreamWaitEvent(p->h2d_stream, p->ev_comp[slot], 0));  // x slot free again
-    CDAN_CUDA_OK(cudaMemcpyAsync(xs, x_host + size_t(n0) * img_floats, bytes, cudaMemcpyHostToDevice, p->h2d_stream));
+    CDAN_CUDA_OK(cudaMemcpyAsync(u8 ? (void*)xu : (void*)xs, (const char*)x_host + size_t(n0) * img_host_bytes, bytes,
+                                 cudaMemcpyHostToDevice, p->h2d_stream));
     CDAN_CUDA_OK(cudaEventRecord(p->ev_h2d[slot], p->h2d_stream));
     CDAN_CUDA_OK(cudaStreamWaitEvent(p->own_stream, p->ev_h2d[slot], 0));
     if (k >= 2) CDAN_CUDA_OK(cudaStreamWaitEvent(p->own_stream, p->ev_d2h[slot], 0));      // y slot drained
+    if (u8) CDAN_TRY(normalize_u8_launch(xu, xs, nb, H, W, p->own_stream));
     CDAN_TRY(forward_impl(p, p->own_stream, xs, ys, nb, H, W));
+    if (u8) CDAN_TRY(quantize_u8_launch(ys, yu, nb, H, W, p->own_stream));
     CDAN_CUDA_OK(cudaEventRecord(p->ev_comp[slot], p->own_stream));
     CDAN_CUDA_OK(cudaStreamWaitEvent(p->d2h_stream, p->ev_comp[slot], 0));
-    CDAN_CUDA_OK(cudaMemcpyAsync(y_host + size_t(n0) * img_floats, ys, bytes, cudaMemcpyDeviceToHost, p->d2h_stream));
+    CDAN_CUDA_OK(cudaMemcpyAsync((char*)y_host + size_t(n0) * img_host_bytes, u8 ? (const void*)yu : (const void*)ys, bytes,
+                                 cudaMemcpyDeviceToHost, p->d2h_stream));
     CDAN_CUDA_OK(cudaEventRecord(p->ev_d2h[slot], p->d2h_stream));
   }
   CDAN_CUDA_OK(cudaStreamSynchronize(p->d2h_stream));
   return 0;
+}
+
+int cdan_forward_host(cdan_plan* p, const float* x_host, float* y_host, int N, int H, int W) {
+  if (!p || !x_host || !y_host) return fail("cdan_forward_host: NULL argument");
+  return forward_host_impl(p, x_host, y_host, N, H, W, false);
+}
+
+int cdan_forward_host_u8(cdan_plan* p, const unsigned char* x_host, unsigned char* y_host, int N, int H, int W) {
+  if (!p || !x_host || !y_host) return fail("cdan_forward_host_u8: NULL argument");
+  return forward_host_impl(p, x_host, y_host, N, H, W, true);
 }
 
 int cdan_stage_read(cdan_plan* p, void* stream, const char* name, float* dst, int64_t shape_out[4]) {

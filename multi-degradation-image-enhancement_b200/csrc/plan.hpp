@@ -73,7 +73,7 @@ struct cdan_plan {
   // host-buffer entry point: copy streams, per-slot events and double-buffered device staging (sub-batch pipeline)
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
-  float* host_stage = nullptr;  // [2 slots][x | y]
+  void* host_stage = nullptr;   // [2 slots][fp32 x | fp32 y | u8 x | u8 y]
   size_t host_stage_bytes = 0;
   int host_chunk = 16;          // images per full pipeline step (option "host_chunk")
   // optional per-launch CUDA-event timing ("profile" option): label -> accumulated ms / count

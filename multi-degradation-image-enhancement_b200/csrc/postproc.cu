@@ -305,6 +305,41 @@ int quantize_u8_launch(const float* x, uint8_t* y, int N, int H, int W, cudaStre
   return 0;
 }
 
+// Same-size input normalisation for the uint8 host path (reference data/dataset.py:86-92: the uint8 HWC image goes through
+// `A.Normalize(mean 0, std 1, max_pixel_value 255)` + `ToTensorV2`): interleaved uint8 [N,H,W,3] -> planar fp32
+// [N,3,H,W], x = float(u8) * float32(1/255).  One thread per four pixels: three 32-bit loads, three float4 stores.
+__global__ void __launch_bounds__(256) normalize_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t HW,
+                                                            size_t quads_per_image, size_t total_quads) {
+  const float inv255 = 1.0f / 255.0f;
+  for (size_t q = blockIdx.x * size_t(blockDim.x) + threadIdx.x; q < total_quads; q += size_t(gridDim.x) * blockDim.x) {
+    const size_t n = q / quads_per_image, p = (q - n * quads_per_image) * 4;
+    const uint32_t* in = reinterpret_cast<const uint32_t*>(src + (n * HW + p) * 3);
+    const uint32_t w0 = in[0], w1 = in[1], w2 = in[2];
+    uint32_t b[12];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      b[i] = (w0 >> (8 * i)) & 0xffu;
+      b[4 + i] = (w1 >> (8 * i)) & 0xffu;
+      b[8 + i] = (w2 >> (8 * i)) & 0xffu;
+    }
+    float* o = dst + n * 3 * HW + p;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      *reinterpret_cast<float4*>(o + c * HW) = make_float4(float(b[c]) * inv255, float(b[3 + c]) * inv255, float(b[6 + c]) * inv255, float(b[9 + c]) * inv255);
+  }
+}
+
+int normalize_u8_launch(const uint8_t* src, float* dst, int N, int H, int W, cudaStream_t s) {
+  const size_t HW = size_t(H) * W;
+  if (HW % 4 != 0) return fail("normalize_u8: H*W must be a multiple of 4");
+  if (reinterpret_cast<uintptr_t>(dst) % 16 != 0 || reinterpret_cast<uintptr_t>(src) % 4 != 0) return fail("normalize_u8: misaligned buffer");
+  const size_t qpi = HW / 4, total = qpi * N;
+  const int blocks = int(std::min<size_t>((total + 255) / 256, size_t(148) * 16));
+  normalize_u8_kernel<<<std::max(blocks, 1), 256, 0, s>>>(src, dst, HW, qpi, total);
+  CDAN_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // Input side (reference data/dataset.py:86-92 + utils/transforms_factory.py:50-86): uint8 HWC images ->
 // cv2.resize(INTER_LINEAR) -> Normalize(mean 0, std 1, max 255) -> CHW float32.  The arithmetic is OpenCV's fixed-point
 // bilinear for 8-bit images (11-bit weights; resize.cpp HResizeLinear / VResizeLinear), restated and pinned bit-exactly

@@ -14,7 +14,7 @@ _EXTS = (".png", ".jpg", ".jpeg", ".bmp", ".tif", ".tiff", ".webp")
 
 
 def _list_images(folder: str) -> List[str]:
-    return sorted(f for f in os.listdir(folder) if f.lower().endswith(_EXTS))
+    return sorted(f for f in os.listdir(folder) if not f.startswith(".") and f.lower().endswith(_EXTS))
 
 
 class PairedDataset(Dataset):

@@ -58,16 +58,36 @@ def _gray(x: torch.Tensor) -> torch.Tensor:
     return 0.2989 * x[:, 0:1] + 0.5870 * x[:, 1:2] + 0.1140 * x[:, 2:3]
 
 
+def _ssim_torch(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """Differentiable SSIM with torchmetrics' default settings restated (11x11 Gaussian sigma 1.5, k1 0.01, k2 0.03,
+    data range from the batch, reflect padding then crop = statistics over the valid region; parity unpinned, see
+    oracle/metrics_oracle.py).  Used by the 'ssim' loss term when a gradient is required (train_step)."""
+    c = x.shape[1]
+    d = torch.arange(11, dtype=x.dtype, device=x.device) - 5
+    g = torch.exp(-(d * d) / (2 * 1.5 * 1.5))
+    g = g / g.sum()
+    k = (g[:, None] * g[None, :]).expand(c, 1, 11, 11).contiguous()
+    rng = torch.maximum(x.detach().max() - x.detach().min(), y.max() - y.min())
+    c1, c2 = (0.01 * rng) ** 2, (0.03 * rng) ** 2
+    mu_x, mu_y = F.conv2d(x, k, groups=c), F.conv2d(y, k, groups=c)
+    sxx = F.conv2d(x * x, k, groups=c) - mu_x * mu_x
+    syy = F.conv2d(y * y, k, groups=c) - mu_y * mu_y
+    sxy = F.conv2d(x * y, k, groups=c) - mu_x * mu_y
+    ssim = ((2 * mu_x * mu_y + c1) * (2 * sxy + c2)) / ((mu_x * mu_x + mu_y * mu_y + c1) * (sxx + syy + c2))
+    return ssim.flatten(1).mean(1).mean()
+
+
 def _need(targets, name):
     if targets is None:
         raise ValueError(f"{name} loss requires targets (paired dataset).")
 
 
 def build_loss_pipeline(loss_cfg: Optional[Dict[str, Any]], device: str) -> LossPipeline:
-    if not loss_cfg or not loss_cfg.get("enabled", True):
-        return LossPipeline([])
+    if not loss_cfg or not loss_cfg.get("enabled", True):  # reference :117-123: default fallback = plain MSE
+        loss_cfg = {"terms": [{"name": "mse", "weight": 1.0, "args": {}}]}
+    terms_cfg = loss_cfg.get("terms", []) or [{"name": "mse", "weight": 1.0, "args": {}}]
     terms: List[LossTerm] = []
-    for t in loss_cfg.get("terms", []) or []:
+    for t in terms_cfg:
         name, weight = t["name"], float(t.get("weight", 1.0))
         args, mode = t.get("args", {}) or {}, t.get("mode", "paired")
         if name == "mse":
@@ -95,9 +115,8 @@ def build_loss_pipeline(loss_cfg: Optional[Dict[str, Any]], device: str) -> Loss
         elif name == "ssim":
             def fn(outputs, targets, inputs=None):
                 _need(targets, "ssim")
-                if outputs.requires_grad:
-                    raise RuntimeError("cdan_b200: the native SSIM kernel has no backward; the 'ssim' loss term is "
-                                       "available for evaluation only (training is outside the accelerated path)")
+                if outputs.requires_grad or not outputs.is_cuda:
+                    return 1.0 - _ssim_torch(outputs, targets)  # training / CPU: differentiable torch composition
                 import cdan_b200_native as native
                 return 1.0 - native.psnr_ssim(outputs, targets)[1]
         elif name in ("vgg_perceptual", "lpips"):

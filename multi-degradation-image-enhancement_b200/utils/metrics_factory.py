@@ -24,33 +24,45 @@ class MetricItem:
 
 
 class _PsnrSsim:
-    """Caches the fused (psnr, ssim) result for the most recent (outputs, targets) pair."""
+    """Fused (psnr, ssim) of ONE MetricsPipeline.__call__: both items of a call share one native reduction.  The result
+    is tied to the identity of the tensor objects of that call (strong references, compared with `is`) and dropped when the
+    call returns — never keyed on data pointers, which the caching allocator reuses for the next same-shaped batch."""
 
     def __init__(self):
-        self._key, self._val = None, (float("nan"), float("nan"))
+        self.reset()
+
+    def reset(self):
+        self._outputs, self._targets, self._version, self._val = None, None, None, None
 
     def __call__(self, outputs, targets):
         if targets is None:
             raise ValueError("psnr/ssim metrics require targets (paired dataset).")
-        key = (outputs.data_ptr(), targets.data_ptr(), outputs._version, tuple(outputs.shape))
-        if key != self._key:
+        if self._val is None or outputs is not self._outputs or targets is not self._targets or \
+                (outputs._version, targets._version) != self._version:
             self._val = _native.psnr_ssim(outputs, targets)
-            self._key = key
+            self._outputs, self._targets, self._version = outputs, targets, (outputs._version, targets._version)
         return self._val
 
 
 class MetricsPipeline:
-    def __init__(self, metrics: Dict[str, MetricItem]):
+    def __init__(self, metrics: Dict[str, MetricItem], fused: Optional[_PsnrSsim] = None):
         self.metrics = metrics
+        self._fused = fused
 
     def __call__(self, outputs, targets=None, inputs=None, is_paired: bool = True) -> Dict[str, torch.Tensor]:
         out: Dict[str, torch.Tensor] = {}
-        for name, item in self.metrics.items():
-            if (item.mode == "paired") != bool(is_paired):
-                continue
-            val = item.fn(outputs=outputs, targets=targets, inputs=inputs)
-            val = torch.as_tensor(val)
-            out[name] = val.mean() if val.ndim else val
+        if self._fused is not None:
+            self._fused.reset()
+        try:
+            for name, item in self.metrics.items():
+                if (item.mode == "paired") != bool(is_paired):
+                    continue
+                val = item.fn(outputs=outputs, targets=targets, inputs=inputs)
+                val = torch.as_tensor(val)
+                out[name] = val.mean() if val.ndim else val
+        finally:
+            if self._fused is not None:
+                self._fused.reset()  # the shared result lives for this call only
         return out
 
 
@@ -69,4 +81,4 @@ def build_metrics_pipeline(metrics_cfg: Optional[Dict[str, Any]], device: str) -
             warnings.warn("cdan_b200: metric 'lpips' needs pretrained AlexNet weights (unavailable offline); skipped")
         else:
             raise ValueError(f"Unknown metric: {name}")
-    return MetricsPipeline(metrics)
+    return MetricsPipeline(metrics, fused)

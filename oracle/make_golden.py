@@ -36,26 +36,9 @@ def subsample_index(numel: int) -> np.ndarray:
 
 
 def import_reference(ref_root: str):
-    """Import the reference's models package without polluting sys.modules for the caller."""
-    saved = {k: v for k, v in sys.modules.items() if k == "models" or k.startswith("models.") or k == "utils"
-             or k.startswith("utils.")}
-    for k in saved:
-        del sys.modules[k]
-    saved_path = list(sys.path)
-    # the drop-in package mirrors the reference's module names; keep it off the path while importing the reference
-    sys.path[:] = [ref_root] + [p for p in sys.path if "multi-degradation-image-enhancement_b200" not in p]
-    try:
-        import importlib
-        cdan_mod = importlib.import_module("models.cdan")
-        pp_mod = importlib.import_module("utils.post_processing")
-        ppf_mod = importlib.import_module("utils.postprocessing_factory")
-    finally:
-        sys.path[:] = saved_path
-        for k in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "utils"
-                  or k.startswith("utils.")]:
-            del sys.modules[k]
-        sys.modules.update(saved)
-    return cdan_mod, pp_mod, ppf_mod
+    """Import the reference's modules from `ref_root` without polluting sys.modules for the caller."""
+    from oracle.build_ref import load_ref
+    return load_ref(ref_root)
 
 
 def run_reference(cdan_mod, sd, x):
@@ -104,6 +87,32 @@ def main():
             blob["stage/" + sname + "/stats"] = np.array([flat.sum(), np.abs(flat).sum(), flat.max(), flat.min()])
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), **blob)
         print(name, "out range", float(y.min()), float(y.max()), "std", float(y.std()))
+
+    # torch's own bf16-autocast error of the REFERENCE on the same weights / inputs (the bf16 plan's bound is
+    # "<= 2x this floor"); the 1080p rows take a few minutes of CPU time
+    import json
+    floors = {}
+    floor_cases = [("stress_2x64x96", stress_state_dict(1234), ramp_input(2, 64, 96, seed=7)),
+                   ("default_2x64x96", default_state_dict(42), uniform_input(2, 64, 96, seed=42)),
+                   ("stress_1x1080x1920", stress_state_dict(1234), ramp_input(1, 1080, 1920, seed=21)),
+                   ("default_1x1080x1920", default_state_dict(42), uniform_input(1, 1080, 1920, seed=42)),
+                   ("stress_8x256x256", stress_state_dict(1234), ramp_input(8, 256, 256, seed=5)),
+                   ("default_8x256x256", default_state_dict(42), uniform_input(8, 256, 256, seed=42))]
+    for name, sd, x in floor_cases:
+        net = cdan_mod.CDAN()
+        net.load_state_dict(sd, strict=True)
+        net.eval()
+        with torch.no_grad():
+            y32 = net(x)
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                y16 = net(x).float()
+        err = (y16 - y32).abs().max().item()
+        mse = ((y16.double() - y32.double()) ** 2).mean().item()
+        floors[name] = {"max_abs": err, "psnr_db": 10.0 * np.log10(1.0 / mse)}
+        print("bf16 autocast floor", name, floors[name])
+    with open(os.path.join(out_dir, "bf16_autocast_floor.json"), "w") as fh:
+        json.dump({"what": "reference CDAN on CPU: torch.autocast(bfloat16) vs fp32, same weights and inputs "
+                           "(oracle/make_golden.py)", "cases": floors}, fh, indent=1)
 
     # post-processing goldens (utils/post_processing.py through utils/postprocessing_factory.py)
     g = torch.Generator().manual_seed(11)

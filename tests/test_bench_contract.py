@@ -1,4 +1,4 @@
-"""bench.py contract checks that need no GPU: the reference arm (CPU oracle port) prints exactly ONE JSON line on stdout
+"""bench.py contract checks that need no GPU: the reference arm (the reference's own CPU forward from oracle/_ref, else the oracle port) prints exactly ONE JSON line on stdout
 with the keys the driver reads; our arm refuses to run without a CUDA device (no CPU fallback)."""
 import json
 import os
@@ -21,7 +21,8 @@ def test_reference_arm_prints_one_json_line_with_contract_keys():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "MP/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
     assert d["metric"].startswith("megapixels/sec") and d["value"] > 0 and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle.build_ref import ref_available
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_available() else "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 
