@@ -50,7 +50,7 @@ CDAN_API int cdan_plan_destroy(cdan_plan* plan);
 CDAN_API int cdan_plan_load_weights(cdan_plan* plan, int n, const char* const* keys, const void* const* ptrs,
                            const int64_t* numels);
 
-/* Options: "host_chunk" = images per step of cdan_forward_host's copy/compute pipeline (default 16);
+/* Options: "host_chunk" = images per step of the host-buffer copy/compute pipeline (default 0 = auto: 16 x 1080p of pixels);
  *          "conv_impl" = 0 auto (tcgen05 where supported), 1 force CUDA-core path;
  *          "profile"   = 1 brackets every launch group with CUDA events on the launching stream. */
 CDAN_API int cdan_plan_set_option(cdan_plan* plan, const char* name, int value);

@@ -95,6 +95,10 @@ int pack_conv(cdan_plan* p, ConvLayer& L, const float* w, const float* bias, int
   }
   CDAN_TRY(upload(p, hw, &L.d_w));
   CDAN_TRY(upload(p, hb, &L.d_bias));
+  if (Cout <= 16) {  // narrow layers: keep the host image for fused re-packing (final dense block)
+    L.h_w = hw;
+    L.h_bias = hb;
+  }
   if (p->dt == kBF16) CDAN_TRY(umma_pack_create(hw.data(), hb.data(), CinPhys, Cout, L.CoutP, ks, &L.umma));
   return 0;
 }
@@ -108,6 +112,8 @@ int pack_pre(cdan_plan* p, ConvLayer& L, const std::vector<double>& s, const std
   }
   CDAN_TRY(upload(p, hs, &L.d_pre_s));
   CDAN_TRY(upload(p, ht, &L.d_pre_t));
+  L.h_pre_s = hs;
+  L.h_pre_t = ht;
   return 0;
 }
 
@@ -205,6 +211,8 @@ void free_weights(cdan_plan* p) {
     umma_pack_destroy(L.umma);
     L = ConvLayer{};
   }
+  fused_fd_pack_destroy(p->fd_fused);
+  p->fd_fused = nullptr;
   p->loaded = false;
 }
 
@@ -223,13 +231,18 @@ bool dense_hybrid_enabled() {
                         !(getenv("CDAN_CONV_STREAM") && atoi(getenv("CDAN_CONV_STREAM")) == 0);
   return v;
 }
+// CDAN_FD_FUSED=0 runs the final dense block layer by layer (A/B switch and the source of the "dec.final_in" stage tap).
+bool fd_fused_enabled() {
+  static const bool v = !(getenv("CDAN_FD_FUSED") && atoi(getenv("CDAN_FD_FUSED")) == 0);
+  return v;
+}
 int fd_ld() {
   static const int v = getenv("CDAN_FD_LD") ? atoi(getenv("CDAN_FD_LD")) : 128;
   return v;
 }
 
 // ------------------------------------------------------------------------------------------ workspace
-size_t carve(Buffers& b, char* base, DType dt, int N, int H, int W) {
+size_t carve(Buffers& b, char* base, DType dt, int N, int H, int W, bool fd_fused) {
   const size_t es = dt == kF32 ? 4 : 2;
   const size_t p1 = size_t(N) * H * W, p2 = p1 / 4, p4 = p1 / 16, p8 = p1 / 64;
   size_t off = 0;
@@ -256,7 +269,7 @@ size_t carve(Buffers& b, char* base, DType dt, int N, int H, int W) {
   b.U3 = take(p2 * 64 * es);
   b.C3 = take(p2 * 64 * es);
   b.T4 = take(p2 * 8 * es);
-  b.FD = take(p1 * size_t(fd_ld()) * es);  // final dense block concat: 3 input channels padded to 16, then 4 x 16
+  b.FD = take(fd_fused ? 0 : p1 * size_t(fd_ld()) * es);  // final dense block concat: 3 input channels padded to 16, then 4 x 16
   size_t sc = 0;
   sc = std::max(sc, cbam_scratch_floats(N, 512, H / 8, W / 8));
   sc = std::max(sc, cbam_scratch_floats(N, 256, H / 8, W / 8));
@@ -267,9 +280,12 @@ size_t carve(Buffers& b, char* base, DType dt, int N, int H, int W) {
   return off;
 }
 
+bool use_fd_fused(const cdan_plan* p) { return p->dt == kBF16 && p->conv_impl == 0 && p->fd_fused && p->fd_fused_on && fd_fused_enabled(); }
+
 int ensure_workspace(cdan_plan* p, int N, int H, int W) {
   Buffers probe{};
-  const size_t bytes = carve(probe, nullptr, p->dt, N, H, W);
+  const bool fused = use_fd_fused(p);
+  const size_t bytes = carve(probe, nullptr, p->dt, N, H, W, fused);
   if (bytes > p->ws_bytes) {
     if (p->ws) CDAN_CUDA_OK(cudaFree(p->ws));
     p->ws = nullptr;
@@ -277,7 +293,7 @@ int ensure_workspace(cdan_plan* p, int N, int H, int W) {
     CDAN_CUDA_OK(cudaMalloc(&p->ws, bytes));
     p->ws_bytes = bytes;
   }
-  carve(p->buf, (char*)p->ws, p->dt, N, H, W);
+  carve(p->buf, (char*)p->ws, p->dt, N, H, W, fused);
   return 0;
 }
 
@@ -396,6 +412,30 @@ int run_up_add(cdan_plan* p, int cbam_slot, const void* a, int a_ld, const void*
   return 0;
 }
 
+void fill_stages(cdan_plan* p, int ld1, int ld2, int ld3, int fdl) {
+  Buffers& b = p->buf;
+  const int H = p->H, W = p->W;
+  const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8;
+  auto& st = p->stages;
+  st.clear();
+  st["enc.out1"] = {b.D1, 64, ld1, H2, W2};
+  st["enc.dense1"] = {b.DN1, 64, 64, H2, W2};
+  st["enc.out2"] = {b.D2, 128, ld2, H4, W4};
+  st["enc.dense2"] = {b.DN2, 128, 128, H4, W4};
+  st["enc.out3"] = {b.D3, 256, ld3, H8, W8};
+  st["enc.dense3"] = {b.DN3, 256, 256, H8, W8};
+  st["enc.conv4"] = {b.E4, 512, 512, H8, W8};
+  st["bottleneck"] = {b.B0, 512, 512, H8, W8};
+  st["dec.bn1"] = {b.T1, 256, 256, H8, W8};
+  st["dec.gated1"] = {b.C1, 256, 256, H8, W8};
+  st["dec.bn2"] = {b.T2, 128, 128, H8, W8};
+  st["dec.gated2"] = {b.C2, 128, 128, H4, W4};
+  st["dec.bn3"] = {b.T3, 64, 64, H4, W4};
+  st["dec.gated3"] = {b.C3, 64, 64, H2, W2};
+  st["dec.bn4"] = {b.T4, 3, 8, H2, W2};
+  if (fdl) st["dec.final_in"] = {b.FD, 3, fdl, H, W};  // not materialised by the fused final dense block
+}
+
 int forward_impl(cdan_plan* p, cudaStream_t s, const float* x, float* y, int N, int H, int W) {
   if (!p->loaded) return fail("cdan_forward: no weights loaded (call cdan_plan_load_weights first)");
   if (N <= 0 || H <= 0 || W <= 0) return fail("cdan_forward: empty input");
@@ -437,6 +477,15 @@ int forward_impl(cdan_plan* p, cudaStream_t s, const float* x, float* y, int N, 
   CDAN_TRY(run_up_add(p, 3, b.T3, 64, b.D1, ld1, b.U3, N, H2, W2, 1, s));
   CDAN_TRY(run_cbam(p, 3, b.U3, b.DN1, b.C3, N, H2, W2, true, s));
   CDAN_TRY(run_conv(p, DEC4, N, H2, W2, b.C3, 64, b.T4, 8, 0, s));
+  if (use_fd_fused(p)) {
+    // bilinear x2 + x, the final DenseBlock(3,3,16,4) and the sigmoid as ONE kernel (dense_fused.cu): the 67-channel
+    // full-resolution concat never exists in HBM
+    SpanGuard span(p, s, "conv|decoder.final_dense|fused");
+    CDAN_TRY(fused_fd_launch(*p->fd_fused, b.T4, 8, x, y, N, H, W, s));
+    p->launches += 1;
+    fill_stages(p, ld1, ld2, ld3, 0);
+    return 0;
+  }
   // The final dense block's concat buffer is group-planar on the tensor-core path, NHWC otherwise.
   const bool fd_planar = dt == kBF16 && p->conv_impl == 0 && fd_planar_enabled();
   const int fdl = fd_planar ? 16 : fd_ld();
@@ -446,24 +495,7 @@ int forward_impl(cdan_plan* p, cudaStream_t s, const float* x, float* y, int N, 
   if (fd_planar) CDAN_TRY(run_dense_planar(p, FDL0, N, H, W, b.FD, s, y));
   else CDAN_TRY(run_dense(p, FDL0, N, H, W, b.FD, fd_ld(), 16, nullptr, 3, s, y));
 
-  auto& st = p->stages;
-  st.clear();
-  st["enc.out1"] = {b.D1, 64, ld1, H2, W2};
-  st["enc.dense1"] = {b.DN1, 64, 64, H2, W2};
-  st["enc.out2"] = {b.D2, 128, ld2, H4, W4};
-  st["enc.dense2"] = {b.DN2, 128, 128, H4, W4};
-  st["enc.out3"] = {b.D3, 256, ld3, H8, W8};
-  st["enc.dense3"] = {b.DN3, 256, 256, H8, W8};
-  st["enc.conv4"] = {b.E4, 512, 512, H8, W8};
-  st["bottleneck"] = {b.B0, 512, 512, H8, W8};
-  st["dec.bn1"] = {b.T1, 256, 256, H8, W8};
-  st["dec.gated1"] = {b.C1, 256, 256, H8, W8};
-  st["dec.bn2"] = {b.T2, 128, 128, H8, W8};
-  st["dec.gated2"] = {b.C2, 128, 128, H4, W4};
-  st["dec.bn3"] = {b.T3, 64, 64, H4, W4};
-  st["dec.gated3"] = {b.C3, 64, 64, H2, W2};
-  st["dec.bn4"] = {b.T4, 3, 8, H2, W2};
-  st["dec.final_in"] = {b.FD, 3, fdl, H, W};
+  fill_stages(p, ld1, ld2, ld3, fdl);
   return 0;
 }
 
@@ -523,8 +555,12 @@ int cdan_plan_set_option(cdan_plan* p, const char* name, int value) {
     return 0;
   }
   if (!strcmp(name, "host_chunk")) {
-    if (value < 1) return fail("host_chunk must be >= 1");
+    if (value < 0) return fail("host_chunk must be >= 0 (0 = auto)");
     p->host_chunk = value;
+    return 0;
+  }
+  if (!strcmp(name, "fd_fused")) {
+    p->fd_fused_on = value != 0;
     return 0;
   }
   if (!strcmp(name, "conv_impl")) {
@@ -563,6 +599,15 @@ int cdan_plan_load_weights(cdan_plan* p, int n, const char* const* keys, const v
   if (!rc) rc = load_cbam(p, sd, 1, "decoder.cbam1", 256);
   if (!rc) rc = load_cbam(p, sd, 2, "decoder.cbam2", 128);
   if (!rc) rc = load_cbam(p, sd, 3, "decoder.cbam3", 64);
+  if (!rc && p->dt == kBF16) {
+    FusedFdLayer fl[5];
+    for (int i = 0; i < 5; ++i) {
+      const ConvLayer& L = p->conv[FDL0 + i];
+      fl[i].Cin = L.Cin; fl[i].CoutP = L.CoutP;
+      fl[i].w = L.h_w.data(); fl[i].bias = L.h_bias.data(); fl[i].pre_s = L.h_pre_s.data(); fl[i].pre_t = L.h_pre_t.data();
+    }
+    rc = fused_fd_pack_create(fl, &p->fd_fused);
+  }
   if (rc) {
     free_weights(p);
     return rc;
@@ -575,7 +620,7 @@ int cdan_workspace_bytes(cdan_plan* p, int N, int H, int W, size_t* bytes_out) {
   if (!p || !bytes_out) return fail("cdan_workspace_bytes: NULL argument");
   if (N <= 0 || H <= 0 || W <= 0 || H % 8 || W % 8) return fail("cdan_workspace_bytes: H and W must be positive multiples of 8");
   Buffers b{};
-  *bytes_out = carve(b, nullptr, p->dt, N, H, W);
+  *bytes_out = carve(b, nullptr, p->dt, N, H, W, use_fd_fused(p));
   return 0;
 }
 
@@ -601,7 +646,12 @@ static int forward_host_impl(cdan_plan* p, const void* x_host, void* y_host, int
       CDAN_CUDA_OK(cudaEventCreateWithFlags(&p->ev_d2h[i], cudaEventDisableTiming));
     }
   }
-  const int cb = std::max(1, std::min(N, p->host_chunk));
+  // images per full pipeline step: option "host_chunk", or (0 = auto) as many images as make up 16 x 1080p worth of
+  // pixels, so that small images are not run as launch-bound forwards of a handful of images
+  int chunk = p->host_chunk;
+  if (chunk <= 0) chunk = int(std::max<size_t>(1, (size_t(16) * 1080 * 1920) / (size_t(H) * W)));
+  if (chunk >= N && N >= 8) chunk = (N + 1) / 2;  // keep at least two steps so that copies overlap compute
+  const int cb = std::max(1, std::min(N, chunk));
   const size_t img_floats = size_t(3) * H * W, slot_floats = size_t(cb) * img_floats;
   // device staging per slot: fp32 x | fp32 y | (u8 path) u8 x | u8 y
   const size_t slot_bytes = 2 * slot_floats * sizeof(float) + (u8 ? 2 * align_up(slot_floats, 256) : 0);

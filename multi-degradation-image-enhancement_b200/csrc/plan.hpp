@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "conv.cuh"
+#include "dense_fused.cuh"
 #include "kernels.cuh"
 
 namespace cdan {
@@ -34,6 +35,8 @@ struct ConvLayer {
   float* d_pre_s = nullptr;  // fp32 [Cin] pre-activation scale (dense layers) or null
   float* d_pre_t = nullptr;
   UmmaPack* umma = nullptr;
+  // host copies of the packed tensors (kept for the layers a fused kernel re-packs)
+  std::vector<float> h_w, h_bias, h_pre_s, h_pre_t;
 };
 
 struct CbamLayer {
@@ -62,6 +65,8 @@ struct cdan_plan {
   bool loaded = false;
   cdan::ConvLayer conv[cdan::kNumConv];
   cdan::CbamLayer cbam[4];
+  bool fd_fused_on = true;                // option "fd_fused"
+  cdan::FusedFdPack* fd_fused = nullptr;  // final dense block as one kernel (bf16 tensor-core plans)
   std::vector<void*> owned;
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -75,7 +80,7 @@ struct cdan_plan {
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   void* host_stage = nullptr;   // [2 slots][fp32 x | fp32 y | u8 x | u8 y]
   size_t host_stage_bytes = 0;
-  int host_chunk = 16;          // images per full pipeline step (option "host_chunk")
+  int host_chunk = 0;           // images per full pipeline step (option "host_chunk"; 0 = auto: 16 x 1080p of pixels)
   // optional per-launch CUDA-event timing ("profile" option): label -> accumulated ms / count
   int profile = 0;
   struct Span { std::string label; cudaEvent_t e0, e1; };
