@@ -34,6 +34,8 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -50,34 +52,50 @@ struct FusedFdPack {
 namespace {
 
 constexpr int kRowBytes = 4096;  // one operand row: 128 pixels x 16 channels bf16
-constexpr int kG0Depth = 8;      // shared ring of the F0 versions (released by all five consumers)
 constexpr int kValidW = 120;     // output columns per strip
-// Version rings of groups 1..4, one per (consumer c' in 1..4 [4 = transition], group g in 1..c'), enumerated c' major.
-__host__ __device__ constexpr int ring_depth(int cp, int g) { return cp <= 3 ? cp - g + 3 : 3; }
+#ifndef CDAN_FUSED_SLEEP_NS
+#define CDAN_FUSED_SLEEP_NS 32
+#endif
+constexpr uint32_t kSleepNs = CDAN_FUSED_SLEEP_NS;  // back-off between mbarrier polls
+// Ring depths (rows).  G0 is released by all four layers; version ring (c', g) feeds layer c' with group g.  A ring has to
+// hold the structural lag between its producer and its consumer (c' - g + 1 rows for the version rings, 3 rows for G0)
+// PLUS the rows that pass while the chain in between runs (two hand-offs per layer), hence deeper rings for far consumers.
+constexpr int kG0Depth = 11;
+__host__ __device__ constexpr int ring_depth(int cp, int g) { return 3 + 2 * (cp - g); }
 __host__ __device__ constexpr int ring_base(int cp, int g) {
   int b = kG0Depth;
-  for (int c = 1; c <= 4; ++c)
+  for (int c = 1; c <= 3; ++c)
     for (int gg = 1; gg <= c; ++gg) {
       if (c == cp && gg == g) return b;
       b += ring_depth(c, gg);
     }
   return b;
 }
-__host__ __device__ constexpr int ring_id(int cp, int g) { return cp * (cp - 1) / 2 + (g - 1); }
-constexpr int kRowSlots = ring_base(5, 1);  // 42
-// Parameter blob (global -> shared by one bulk copy): weights | activation tables | bias
-constexpr int kWLayerBlock = 48 * 32;                                    // (layer, group, tap): 48 rows x 32 B
+__host__ __device__ constexpr int ring_id(int cp, int g) { return cp * (cp - 1) / 2 + (g - 1); }  // 0..5
+constexpr int kRowSlots = ring_base(4, 1);  // 37
+// closed forms used in the kernel (registers are scarce: 80 per thread), checked against the definitions above
+__host__ __device__ constexpr int ring_base_fast(int cp, int g) {
+  return kG0Depth + (cp == 1 ? 0 : (cp == 2 ? (g == 1 ? 3 : 8) : (g == 1 ? 11 : (g == 2 ? 18 : 23))));
+}
+static_assert(ring_base_fast(1, 1) == ring_base(1, 1) && ring_base_fast(2, 1) == ring_base(2, 1) && ring_base_fast(2, 2) == ring_base(2, 2) &&
+              ring_base_fast(3, 1) == ring_base(3, 1) && ring_base_fast(3, 2) == ring_base(3, 2) && ring_base_fast(3, 3) == ring_base(3, 3), "ring layout");
+// Transition partial sums: fp32 [row][ring index][4] (3 output channels), written by the loader (bias + F0 term), updated by
+// the four epilogues in layer order, finished (sigmoid + store) by the last one.
+constexpr int kTsDepth = 13, kTsRowBytes = 128 * 16;
+// Parameter blob (global -> shared by one bulk copy): weights | activation tables | transition parameters | bias
+constexpr int kWLayerBlock = 48 * 32;  // (layer, group, tap): 48 rows x 32 B, SWIZZLE_32B
 __host__ __device__ constexpr int w_layer_off(int c, int g, int s) { return ((c * (c + 1) / 2 + g) * 3 + s) * kWLayerBlock; }
-constexpr int kWTOff = 30 * kWLayerBlock;                                 // transition: 5 blocks of 16 rows x 32 B
-constexpr int kTabOff = kWTOff + 5 * 512;                                 // 10 rings x (sc 32 B | sh 32 B)
-constexpr int kG0TabOff = kTabOff + 10 * 64;                              // sc 32 B | sh 32 B
-constexpr int kBiasOff = kG0TabOff + 64;                                  // 5 x 16 fp32
+constexpr int kTabOff = 30 * kWLayerBlock;   // 6 rings x (sc 32 B | sh 32 B), bf16
+constexpr int kG0TabOff = kTabOff + 6 * 64;  // sc 32 B | sh 32 B: K slot 3c+ch of the four layers
+constexpr int kTActOff = kG0TabOff + 64;     // transition pre-activation, bf16: sc[80] | sh[80] (physical channels)
+constexpr int kTWOff = kTActOff + 320;       // transition weights as fp32 (bf16-rounded values): [5 groups][3 outputs][16 ch]
+constexpr int kBiasOff = kTWOff + 5 * 192;   // 5 x 16 fp32 (4 layers, transition)
 constexpr int kBlobBytes = kBiasOff + 5 * 16 * 4;
 constexpr int kBlobPad = (kBlobBytes + 1023) / 1024 * 1024;
-constexpr int kSmemBytes = kBlobPad + kRowSlots * kRowBytes + 256 + 1024;
-constexpr int kThreads = 29 * 32;
-// TMEM: layer c -> columns [96c, 96c + 96): 4 ring slots + 2 shadow slots of 16 columns; transition: 8 slots from 384.
-constexpr uint32_t kTCol = 384;
+constexpr int kTsOff = kBlobPad + kRowSlots * kRowBytes + 256;
+constexpr int kSmemBytes = kTsOff + kTsDepth * kTsRowBytes + 1024;
+static_assert(kSmemBytes <= 232448 - 2048, "shared memory budget");
+constexpr int kThreads = 24 * 32;  // 4 layer issuers, 4 loader warps, 4 x 4 epilogue warps
 
 struct FParams {
   int N, H, W;
@@ -87,7 +105,14 @@ struct FParams {
   const float* x;  // [N][3][H][W]
   float* out;      // [N][3][H][W]
   const uint8_t* blob;
+  unsigned long long* trace;  // debug (CDAN_FUSED_TRACE=1): clock64 timeline of CTA 0, first item: [role][kTraceRows]
 };
+constexpr int kTraceRows = 96, kTraceRoles = 20;
+#ifdef CDAN_FUSED_TRACE_BUILD
+#define FTRACE(role, row) do { if (P.trace && blockIdx.x == 0 && item == 0 && (row) >= 0 && (row) < kTraceRows) P.trace[(role) * kTraceRows + (row)] = clock64(); } while (0)
+#else
+#define FTRACE(role, row) do { } while (0)
+#endif
 
 struct Seg {
   int n, w0, h0, h1;
@@ -109,74 +134,123 @@ __device__ __forceinline__ int in_hi(const Seg& s, int H, int c) { return c == 4
 
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return (1u << 16) | ((smem_addr & 0x3FFFFu) >> 4); }
 __device__ __forceinline__ uint32_t sw32_off(int idx, int half) { return uint32_t(idx) * 32u + (uint32_t((half ^ (idx >> 2)) & 1) << 4); }
-
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
-               : "r"(taddr)
-               : "memory");
+__device__ __forceinline__ void arrive_a(uint32_t bar_addr) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  const uint4 u = ptx::lds128(addr);
+  return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
 }
 
+// One lane polls, the warp follows: a warp-wide mbarrier.try_wait costs every lane a trip through the barrier unit
+// (~400 cycles per already-completed wait measured in the first version of this kernel).
+__device__ __forceinline__ void wait_l0(uint32_t bar_addr, uint32_t parity, int lane) {
+  if (lane == 0) ptx::mbar_wait_a(bar_addr, parity);
+  __syncwarp();
+}
+
+// Named barrier over the four warps of one role group (ids 1..5; 0 is __syncthreads).  Only ONE thread per group polls
+// mbarriers: every mbarrier event on the SM wakes every thread parked in try_wait, and with 24 polling warps those wake-ups
+// were 70 % of all issued instructions (ncu, profiles/r02_fused_*).  The other 127 threads wait here instead.
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
 struct Smem {
-  uint32_t blob, rows, full, empty, acc_done, acc_free, accT_done, accT_free;  // shared-window addresses
+  uint32_t blob, rows, ts, full, empty, acc_done, acc_free, ts_full, ts_empty;  // shared-window addresses
   uint64_t* w_full;
   uint32_t tmem;
 };
+// barrier arrays: full/empty[kRowSlots]; acc_done/acc_free[4 layers][4 slots]; ts_full[5 stages][kTsDepth] (stage 0 = loader,
+// stage c+1 = epilogue c), ts_empty[kTsDepth]
 
-// A G0 row this consumer does not read still has to be released (the ring slot is freed by all five consumers).
+// SlotPhases::claim_a with the poll done by lane 0 only
+__device__ __forceinline__ void claim_l0(SlotPhases& fp, uint32_t free_bars, int s, int lane) {
+  if ((fp.used >> s) & 1u) {
+    if (lane == 0) ptx::mbar_wait_a(free_bars + 8u * uint32_t(s), (fp.par >> s) & 1u);
+    fp.par ^= 1u << s;
+  }
+  fp.used |= 1u << s;
+}
+
+// A G0 row this consumer does not read still has to be released (the ring slot is freed by all four layers).
 __device__ __forceinline__ void skip_g0(const Smem& S, Ring& g0, int lane) {
-  ptx::mbar_wait_a(S.full + 8u * uint32_t(g0.i), g0.w & 1);
-  if (lane == 0) asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(S.empty + 8u * uint32_t(g0.i)) : "memory");
+  wait_l0(S.full + 8u * uint32_t(g0.i), g0.w & 1, lane);
+  if (lane == 0) arrive_a(S.empty + 8u * uint32_t(g0.i));
   g0.step(kG0Depth);
 }
 
-// ------------------------------------------------------------------------------------------------ MMA issuer, layer C
-template <int C>
-__device__ __forceinline__ void issuer_layer(const FParams& P, const Smem& S, int lane) {
+// ------------------------------------------------------------------------------------------------ MMA issuer of layer C
+// One code path for all four layers (C is a run-time value): the four issuer warps then share their instruction stream —
+// with one specialised copy per layer the kernel's hot code was ~10 distinct streams and instruction fetch dominated.
+__device__ __forceinline__ void issuer_layer(const FParams& P, const Smem& S, const int C, int lane) {
   const uint32_t idesc = ptx::umma_idesc_bf16(128, 48);
   const uint64_t hi = ptx::umma_desc_sw32(0, 256) & 0xffffffff00000000ull;
   const uint32_t acc_done = S.acc_done + 32u * C, acc_free = S.acc_free + 32u * C;
+  const uint32_t wbase = desc_lo(S.blob + w_layer_off(C, 0, 0));
+  const uint32_t dbase = S.tmem + 96u * C;
   Ring g0;
-  Ring vr[C > 0 ? C : 1];
+  Ring vr[3];
   SlotPhases fp;
-  ptx::mbar_wait(S.w_full, 0);
+  ptx::mbar_wait_relaxed(S.w_full, 0);
   for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
     const Seg sg = decode_seg(P, item);
     const int lo0 = in_lo(sg, 0), hi0 = in_hi(sg, P.H, 0), lo = in_lo(sg, C), hi_ = in_hi(sg, P.H, C);
     for (int r = lo0; r < lo; ++r) skip_g0(S, g0, lane);
     for (int j = lo; j < hi_; ++j) {
+      // all waits of the row by lane 0 (phase bookkeeping is warp-uniform register state): the common case — everything
+      // ready — is one batch of non-blocking phase tests issued back to back
       if (j == lo) {
-        fp.claim_a(acc_free, (j - 1) & 3);
-        fp.claim_a(acc_free, j & 3);
+        claim_l0(fp, acc_free, (j - 1) & 3, lane);
+        claim_l0(fp, acc_free, j & 3, lane);
       }
-      fp.claim_a(acc_free, (j + 1) & 3);
-      ptx::mbar_wait_a(S.full + 8u * uint32_t(g0.i), g0.w & 1);
+      {
+        const int sn = (j + 1) & 3;
+        const bool need_claim = (fp.used >> sn) & 1u;
+        if (lane == 0) {
+          bool ok = ptx::mbar_test_a(S.full + 8u * uint32_t(g0.i), g0.w & 1);
+          if (need_claim) ok &= ptx::mbar_test_a(acc_free + 8u * uint32_t(sn), (fp.par >> sn) & 1u);
 #pragma unroll
-      for (int g = 1; g <= C; ++g) ptx::mbar_wait_a(S.full + 8u * uint32_t(ring_base(C, g) + vr[g - 1].i), vr[g - 1].w & 1);
+          for (int g = 1; g <= 3; ++g)
+            if (g <= C) ok &= ptx::mbar_test_a(S.full + 8u * uint32_t(ring_base_fast(C, g) + vr[g - 1].i), vr[g - 1].w & 1);
+          if (!ok) {
+            if (need_claim) ptx::mbar_wait_a(acc_free + 8u * uint32_t(sn), (fp.par >> sn) & 1u);
+            ptx::mbar_wait_a(S.full + 8u * uint32_t(g0.i), g0.w & 1);
+#pragma unroll
+            for (int g = 1; g <= 3; ++g)
+              if (g <= C) ptx::mbar_wait_a(S.full + 8u * uint32_t(ring_base_fast(C, g) + vr[g - 1].i), vr[g - 1].w & 1);
+          }
+        }
+        if (need_claim) fp.par ^= 1u << sn;
+        fp.used |= 1u << sn;
+      }
+      __syncwarp();
       ptx::tc_fence_after_sync();
       if (ptx::elect_one()) {
-        const uint32_t dcol = S.tmem + 96u * C + 16u * uint32_t((j - 1) & 3);
+        const uint32_t dcol = dbase + 16u * uint32_t((j - 1) & 3);
         {
-          const uint32_t a = desc_lo(S.rows + uint32_t(g0.i) * kRowBytes), b = desc_lo(S.blob + w_layer_off(C, 0, 0));
+          const uint32_t a = desc_lo(S.rows + uint32_t(g0.i) * kRowBytes);
 #pragma unroll
-          for (int s = 0; s < 3; ++s) ptx::umma_bf16(dcol, hi | (a + 2u * s), hi | (b + uint32_t(s) * (kWLayerBlock >> 4)), idesc, 1u);
+          for (int s = 0; s < 3; ++s) ptx::umma_bf16(dcol, hi | (a + 2u * s), hi | (wbase + uint32_t(s) * (kWLayerBlock >> 4)), idesc, 1u);
         }
 #pragma unroll
-        for (int g = 1; g <= C; ++g) {
-          const uint32_t a = desc_lo(S.rows + uint32_t(ring_base(C, g) + vr[g - 1].i) * kRowBytes),
-                         b = desc_lo(S.blob + w_layer_off(C, g, 0));
+        for (int g = 1; g <= 3; ++g) {
+          if (g > C) break;
+          const uint32_t a = desc_lo(S.rows + uint32_t(ring_base_fast(C, g) + vr[g - 1].i) * kRowBytes);
+          const uint32_t b = wbase + uint32_t(g) * (3 * kWLayerBlock >> 4);
 #pragma unroll
           for (int s = 0; s < 3; ++s) ptx::umma_bf16(dcol, hi | (a + 2u * s), hi | (b + uint32_t(s) * (kWLayerBlock >> 4)), idesc, 1u);
         }
         ptx::umma_commit_a(S.empty + 8u * uint32_t(g0.i));
 #pragma unroll
-        for (int g = 1; g <= C; ++g) ptx::umma_commit_a(S.empty + 8u * uint32_t(ring_base(C, g) + vr[g - 1].i));
+        for (int g = 1; g <= 3; ++g)
+          if (g <= C) ptx::umma_commit_a(S.empty + 8u * uint32_t(ring_base_fast(C, g) + vr[g - 1].i));
         ptx::umma_commit_a(acc_done + 8u * uint32_t((j - 1) & 3));
+        FTRACE(C, j);
       }
       __syncwarp();
       g0.step(kG0Depth);
 #pragma unroll
-      for (int g = 1; g <= C; ++g) vr[g - 1].step(ring_depth(C, g));
+      for (int g = 1; g <= 3; ++g)
+        if (g <= C) vr[g - 1].step(ring_depth(C, g));
     }
     // the last two accumulator rows of the segment receive no further input
     if (ptx::elect_one()) {
@@ -188,200 +262,221 @@ __device__ __forceinline__ void issuer_layer(const FParams& P, const Smem& S, in
   }
 }
 
-// ------------------------------------------------------------------------------------------------ MMA issuer, transition
-// Program order per step t: G1 row t (opens the accumulator, accumulate = 0), G2 row t-1, G3 row t-2, G4 row t-3, G0 row
-// t-3, then the row is handed to the epilogue.  The order is fixed, so the fp32 summation order of a row never changes.
-__device__ __forceinline__ void issuer_transition(const FParams& P, const Smem& S, int lane) {
-  const uint32_t idesc = ptx::umma_idesc_bf16(128, 16);
-  const uint64_t hi = ptx::umma_desc_sw32(0, 256) & 0xffffffff00000000ull;
-  Ring g0;
-  Ring vr[4];
-  SlotPhases fp;
-  ptx::mbar_wait(S.w_full, 0);
-  for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-    const Seg sg = decode_seg(P, item);
-    const int lo0 = in_lo(sg, 0), hi0 = in_hi(sg, P.H, 0);
-    for (int r = lo0; r < sg.h0; ++r) skip_g0(S, g0, lane);
-    for (int t = sg.h0; t < sg.h1 + 3; ++t) {
-#pragma unroll
-      for (int g = 1; g <= 4; ++g) {
-        const int r = t - (g - 1);
-        if (r < sg.h0 || r >= sg.h1) continue;
-        if (g == 1) fp.claim_a(S.accT_free, r & 7);
-        const uint32_t slot = uint32_t(ring_base(4, g) + vr[g - 1].i);
-        ptx::mbar_wait_a(S.full + 8u * slot, vr[g - 1].w & 1);
-        ptx::tc_fence_after_sync();
-        if (ptx::elect_one()) {
-          ptx::umma_bf16(S.tmem + kTCol + 16u * uint32_t(r & 7), hi | desc_lo(S.rows + slot * kRowBytes),
-                         hi | desc_lo(S.blob + kWTOff + g * 512), idesc, g == 1 ? 0u : 1u);
-          ptx::umma_commit_a(S.empty + 8u * slot);
-        }
-        __syncwarp();
-        vr[g - 1].step(ring_depth(4, g));
-      }
-      const int r = t - 3;
-      if (r >= sg.h0) {
-        ptx::mbar_wait_a(S.full + 8u * uint32_t(g0.i), g0.w & 1);
-        ptx::tc_fence_after_sync();
-        if (ptx::elect_one()) {
-          ptx::umma_bf16(S.tmem + kTCol + 16u * uint32_t(r & 7), hi | desc_lo(S.rows + uint32_t(g0.i) * kRowBytes),
-                         hi | desc_lo(S.blob + kWTOff), idesc, 1u);
-          ptx::umma_commit_a(S.empty + 8u * uint32_t(g0.i));
-          ptx::umma_commit_a(S.accT_done + 8u * uint32_t(r & 7));
-        }
-        __syncwarp();
-        g0.step(kG0Depth);
-      }
-    }
-    for (int r = sg.h1; r < hi0; ++r) skip_g0(S, g0, lane);
-  }
+// ------------------------------------------------------------------------------------------------ epilogue of layer C
+// Also one code path for all layers.  Per output row: drain the accumulator (+ shadow slot) and round it to bf16; write the
+// pre-activated version for every later layer (the layer's bias is folded into the activation shift: relu(s*(v+b)+t) =
+// relu(s*v + (s*b+t))); add this group's term of the 1x1 transition to the fp32 partial-sum ring; the last layer's
+// epilogue finishes the transition (sigmoid, planar fp32 store, models/cdan.py:157).
+// Synchronisation: the group's leader thread does all mbarrier polling and arriving; the four warps meet at a named barrier
+// three times per row.  The kernel is bound by instruction issue (24 warps x a few hundred instructions per row), so this
+// loop is written for instruction count.
+__device__ __forceinline__ uint64_t pack_f2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float sum_f2(uint64_t v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo + hi;
 }
 
-// ------------------------------------------------------------------------------------------------ epilogue, layer C
-template <int C>
-__device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, uint64_t* full, uint64_t* empty, uint64_t* acc_done,
-                                               uint64_t* acc_free, int q, int lane) {
-  constexpr int G = C + 1;   // group this layer produces
-  constexpr int NC = 4 - C;  // consumers: layers C+1..3, then the transition
-  Ring cr[NC];
-  SlotPhases dp;
+__device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, const int C, int q, int lane) {
+  const int G = C + 1;   // group this layer produces
+  const int NC = 3 - C;  // later layers that read it
+  const int bar_id = 1 + C;
+  const bool leader = q == C && lane == 0;  // the groups' leaders sit on different SM sub-partitions
+  const uint32_t acc_free = S.acc_free + 32u * C, acc_done = S.acc_done + 32u * C;
+  // consumer k of this layer's group: layer cp = C + 1 + k reads it through ring (cp, G)
+  auto rbk = [&](int k) { return ring_base_fast(C + 1 + k, G); };
+  auto tabk = [&](int k) { return S.blob + kTabOff + uint32_t(ring_id(C + 1 + k, G)) * 64u; };
+  Ring cr[3];
+  Ring tsr;  // transition partial-sum ring position (rows [h0, h1) of every item, in order)
+  uint32_t dpar = 0;  // acc_done phase parity per slot
   const int L = q * 32 + lane, idx = L + 1;  // output lane L is centred on ring index L + 1
   const bool idx_ok = idx >= G && idx < 128 - G;
-  const uint32_t off[2] = {sw32_off(idx & 127, 0), sw32_off(idx & 127, 1)};
+  const uint32_t off0 = sw32_off(idx & 127, 0), off1 = sw32_off(idx & 127, 1);
   const uint32_t lb = S.tmem + (uint32_t(q * 32) << 16) + 96u * C;
-  ptx::mbar_wait(S.w_full, 0);
-  float bias[16];
-#pragma unroll
-  for (int e = 0; e < 16; ++e) bias[e] = 0.f;
-  {
-    const float* sb = reinterpret_cast<const float*>(__cvta_shared_to_generic(S.blob + kBiasOff)) + C * 16;
-#pragma unroll
-    for (int e = 0; e < 16; ++e) bias[e] = sb[e];
-  }
+  const uint32_t tact_u = S.blob + kTActOff + uint32_t(G) * 32u;  // sc of this group's 16 channels (sh: + 160)
+  const uint32_t tw_u = S.blob + kTWOff + uint32_t(G) * 192u;     // [3 outputs][16 ch] fp32 of this group
+  const uint32_t ts_in = S.ts_full + 8u * uint32_t(C * kTsDepth), ts_out = S.ts_full + 8u * uint32_t((C + 1) * kTsDepth);
+  const uint32_t ts_addr0 = S.ts + uint32_t(idx & 127) * 16u;
+  ptx::mbar_wait_relaxed(S.w_full, 0);
+  const size_t plane = size_t(P.H) * P.W;
   for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
     const Seg sg = decode_seg(P, item);
     const int lo = in_lo(sg, C), hi_ = in_hi(sg, P.H, C);
     const int olo = lo == 0 ? 0 : lo + 1, ohi = hi_ == P.H ? P.H : hi_ - 1;
     const int col = sg.w0 - 4 + idx;
     const bool keep = idx_ok && col >= 0 && col < P.W;
+    float* orow = P.out + size_t(sg.n) * 3 * plane + col;
     for (int i = lo - 1; i <= hi_; ++i) {
       const int slot = i & 3;
-      dp.wait(acc_done, slot);
-      ptx::tc_fence_after_sync();
       const bool valid = i >= olo && i < ohi;
-      bool take[NC];
+      const bool tsrow = i >= sg.h0 && i < sg.h1;  // rows of the transition (always inside the valid range)
+      // rows layer cp reads: [max(0, h0-4+cp), min(H, h1+4-cp)); a valid row is inside the image, so the clipping drops out
+      bool take[3];
 #pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        const int cp = k < NC - 1 ? C + 1 + k : 4;
-        take[k] = valid && i >= in_lo(sg, cp) && i < in_hi(sg, P.H, cp);
-        if (take[k]) ptx::mbar_wait(&empty[ring_base(cp, G) + cr[k].i], (cr[k].w & 1) ^ 1);
+      for (int k = 0; k < 3; ++k) take[k] = k < NC && valid && i >= sg.h0 - 3 + C + k && i < sg.h1 + 3 - C - k;
+      // 0. the leader waits for everything this row needs: the accumulator, a free slot in every consumer ring, and the
+      //    transition partial sums of the earlier stages (all but the first are usually complete already)
+      if (leader) {
+        bool ok = ptx::mbar_test_a(acc_done + 8u * uint32_t(slot), (dpar >> slot) & 1u);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (take[k]) ok &= ptx::mbar_test_a(S.empty + 8u * uint32_t(rbk(k) + cr[k].i), (cr[k].w & 1) ^ 1);
+        if (tsrow) ok &= ptx::mbar_test_a(ts_in + 8u * uint32_t(tsr.i), tsr.w & 1);
+        if (!ok) {
+          ptx::mbar_wait_a(acc_done + 8u * uint32_t(slot), (dpar >> slot) & 1u);
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            if (take[k]) ptx::mbar_wait_a(S.empty + 8u * uint32_t(rbk(k) + cr[k].i), (cr[k].w & 1) ^ 1);
+          if (tsrow) ptx::mbar_wait_a(ts_in + 8u * uint32_t(tsr.i), tsr.w & 1);
+        }
       }
+      dpar ^= 1u << slot;
+      group_sync(bar_id);
+      ptx::tc_fence_after_sync();
+      if (leader) FTRACE(4 + C, i);
       const bool shadow = slot < 2;
       const uint32_t tm = lb + 16u * uint32_t(slot), ts = lb + 16u * uint32_t(4 + slot);
+      // 1. drain the accumulator row (+ its shadow slot), re-zero it
+      uint32_t v[16];
+      if (valid) {
+        ptx::tmem_ld16(tm, v);
+        if (shadow) {
+          uint32_t v2[8];
+          ptx::tmem_ld8(ts, v2);
+          ptx::tmem_wait_ld();
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t v[8];
-        if (valid) {
-          ptx::tmem_ld8(tm + 8u * half, v);
-          if (shadow) {
-            uint32_t v2[8];
-            ptx::tmem_ld8(ts + 8u * half, v2);
-            ptx::tmem_wait_ld();
+          for (int e = 0; e < 8; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(v2[e]));
+          ptx::tmem_ld8(ts + 8u, v2);
+          ptx::tmem_wait_ld();
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(v2[e]));
-          } else {
-            ptx::tmem_wait_ld();
-          }
+          for (int e = 0; e < 8; ++e) v[8 + e] = __float_as_uint(__uint_as_float(v[8 + e]) + __uint_as_float(v2[e]));
+        } else {
+          ptx::tmem_wait_ld();
         }
-        ptx::tmem_st8_zero(tm + 8u * half);
-        if (shadow) ptx::tmem_st8_zero(ts + 8u * half);
-        if (valid) {
-          __nv_bfloat162 raw[4];
+      }
+      ptx::tmem_st16_zero(tm);
+      if (shadow) ptx::tmem_st16_zero(ts);
+      // 2. round to bf16 (the bias is folded into the consumers' activation shifts)
+      __nv_bfloat162 raw[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            raw[e] = __floats2bfloat162_rn(__uint_as_float(v[2 * e]) + bias[8 * half + 2 * e], __uint_as_float(v[2 * e + 1]) + bias[8 * half + 2 * e + 1]);
+      for (int e = 0; e < 8; ++e) raw[e] = __floats2bfloat162_rn(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+      // 3. one pre-activated version per later layer; the next layer's comes first and is released at once together with
+      //    the accumulator row (it is on the critical path of the chain)
+      auto write_version = [&](int k) {
+        const uint32_t tb = tabk(k);
+        const uint4 sc0 = ptx::lds128(tb), sc1 = ptx::lds128(tb + 16u), sh0 = ptx::lds128(tb + 32u), sh1 = ptx::lds128(tb + 48u);
+        const __nv_bfloat162* c0p = reinterpret_cast<const __nv_bfloat162*>(&sc0);
+        const __nv_bfloat162* c1p = reinterpret_cast<const __nv_bfloat162*>(&sc1);
+        const __nv_bfloat162* h0p = reinterpret_cast<const __nv_bfloat162*>(&sh0);
+        const __nv_bfloat162* h1p = reinterpret_cast<const __nv_bfloat162*>(&sh1);
+        uint4 o0, o1;
+        __nv_bfloat162* a0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+        __nv_bfloat162* a1 = reinterpret_cast<__nv_bfloat162*>(&o1);
 #pragma unroll
-          for (int k = 0; k < NC; ++k) {
-            if (!take[k]) continue;
-            const int cp = k < NC - 1 ? C + 1 + k : 4;
-            const uint32_t tab = S.blob + kTabOff + uint32_t(ring_id(cp, G)) * 64u + uint32_t(half) * 16u;
-            const uint4 csc = ptx::lds128(tab), csh = ptx::lds128(tab + 32u);
-            const __nv_bfloat162* sc = reinterpret_cast<const __nv_bfloat162*>(&csc);
-            const __nv_bfloat162* sh = reinterpret_cast<const __nv_bfloat162*>(&csh);
-            uint4 o;
-            __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) a[e] = __hfma2_relu(raw[e], sc[e], sh[e]);
-            if (!keep) o = make_uint4(0u, 0u, 0u, 0u);  // outside the image / the layer's valid range: zero AFTER activation
-            if (idx < 128) ptx::sts128(S.rows + uint32_t(ring_base(cp, G) + cr[k].i) * kRowBytes + off[half], o);
-          }
+        for (int e = 0; e < 4; ++e) {
+          a0[e] = __hfma2_relu(raw[e], c0p[e], h0p[e]);
+          a1[e] = __hfma2_relu(raw[4 + e], c1p[e], h1p[e]);
         }
+        if (!keep) {  // outside the image / the layer's valid range: zero AFTER activation
+          o0 = make_uint4(0u, 0u, 0u, 0u);
+          o1 = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (idx < 128) {
+          const uint32_t base = S.rows + uint32_t(rbk(k) + cr[k].i) * kRowBytes;
+          ptx::sts128(base + off0, o0);
+          ptx::sts128(base + off1, o1);
+        }
+      };
+      if (take[0]) {
+        write_version(0);
+        ptx::fence_proxy_async_smem();
       }
       ptx::tmem_wait_st();
       ptx::tc_fence_before_sync();
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        ptx::mbar_arrive(&acc_free[slot]);
+      group_sync(bar_id);
+      if (leader) {
+        arrive_a(acc_free + 8u * uint32_t(slot));
+        if (take[0]) arrive_a(S.full + 8u * uint32_t(rbk(0) + cr[0].i));
+        FTRACE(13, i);
+      }
+      if (take[1]) write_version(1);
+      if (take[2]) write_version(2);
+      // 4. this group's term of the 1x1 transition (16 channels x 3 outputs, packed fp32 FMAs) on top of the partial sums so
+      //    far (loader: bias + F0 term; earlier layers in order)
+      if (tsrow) {
+        uint64_t av[8];
+        {
+          const uint4 sc0 = ptx::lds128(tact_u), sc1 = ptx::lds128(tact_u + 16u), sh0 = ptx::lds128(tact_u + 160u), sh1 = ptx::lds128(tact_u + 176u);
+          const __nv_bfloat162* c0p = reinterpret_cast<const __nv_bfloat162*>(&sc0);
+          const __nv_bfloat162* c1p = reinterpret_cast<const __nv_bfloat162*>(&sc1);
+          const __nv_bfloat162* h0p = reinterpret_cast<const __nv_bfloat162*>(&sh0);
+          const __nv_bfloat162* h1p = reinterpret_cast<const __nv_bfloat162*>(&sh1);
 #pragma unroll
-        for (int k = 0; k < NC; ++k) {
-          const int cp = k < NC - 1 ? C + 1 + k : 4;
-          if (take[k]) ptx::mbar_arrive(&full[ring_base(cp, G) + cr[k].i]);
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 x0 = __hfma2_relu(raw[e], c0p[e], h0p[e]), x1 = __hfma2_relu(raw[4 + e], c1p[e], h1p[e]);
+            const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&x0), u1 = *reinterpret_cast<const uint32_t*>(&x1);
+            av[e] = pack_f2(bflo(u0), bfhi(u0));
+            av[4 + e] = pack_f2(bflo(u1), bfhi(u1));
+          }
+        }
+        float tt[3];
+#pragma unroll
+        for (int co = 0; co < 3; ++co) {  // weights: [output][16 channels] fp32 per group
+          uint64_t acc = 0ull;
+#pragma unroll
+          for (int h4 = 0; h4 < 4; ++h4) {
+            const uint4 w = ptx::lds128(tw_u + uint32_t(co) * 64u + uint32_t(h4) * 16u);
+            acc = ffma2((uint64_t(w.y) << 32) | w.x, av[2 * h4], acc);
+            acc = ffma2((uint64_t(w.w) << 32) | w.z, av[2 * h4 + 1], acc);
+          }
+          tt[co] = sum_f2(acc);
+        }
+        const uint32_t addr = ts_addr0 + uint32_t(tsr.i) * kTsRowBytes;
+        float4 acc = lds_f4(addr);
+        acc.x += tt[0]; acc.y += tt[1]; acc.z += tt[2];
+        if (C < 3) {
+          if (idx < 128) ptx::sts128(addr, make_uint4(__float_as_uint(acc.x), __float_as_uint(acc.y), __float_as_uint(acc.z), 0u));
+        } else if (idx >= 4 && idx < 124 && col < P.W) {
+          float* o = orow + size_t(i) * P.W;
+          o[0] = 1.0f / (1.0f + __expf(-acc.x));
+          o[plane] = 1.0f / (1.0f + __expf(-acc.y));
+          o[2 * plane] = 1.0f / (1.0f + __expf(-acc.z));
         }
       }
+      if (C == 0 && leader) FTRACE(15, i);
+      // 5. release the remaining versions and the partial sums
+      if (take[1] || tsrow) {
+        ptx::fence_proxy_async_smem();
+        group_sync(bar_id);
+        if (leader) {
+          if (take[1]) arrive_a(S.full + 8u * uint32_t(rbk(1) + cr[1].i));
+          if (take[2]) arrive_a(S.full + 8u * uint32_t(rbk(2) + cr[2].i));
+          if (tsrow) arrive_a(C < 3 ? ts_out + 8u * uint32_t(tsr.i) : S.ts_empty + 8u * uint32_t(tsr.i));
+        }
+      }
+      if (leader) FTRACE(8 + C, i);
 #pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        const int cp = k < NC - 1 ? C + 1 + k : 4;
-        if (take[k]) cr[k].step(ring_depth(cp, G));
-      }
+      for (int k = 0; k < 3; ++k)
+        if (take[k]) cr[k].step(3 + 2 * k);
+      if (tsrow) tsr.step(kTsDepth);
     }
   }
 }
 
-// ------------------------------------------------------------------------------------------------ epilogue, transition
-__device__ __forceinline__ void epilogue_transition(const FParams& P, const Smem& S, uint64_t* accT_done, uint64_t* accT_free, int q,
-                                                    int lane) {
-  SlotPhases dp;
-  const int idx = q * 32 + lane;  // 1x1: output lane = ring index
-  const uint32_t lb = S.tmem + (uint32_t(q * 32) << 16) + kTCol;
-  ptx::mbar_wait(S.w_full, 0);
-  const float* sb = reinterpret_cast<const float*>(__cvta_shared_to_generic(S.blob + kBiasOff)) + 4 * 16;
-  const float b0 = sb[0], b1 = sb[1], b2 = sb[2];
-  const size_t plane = size_t(P.H) * P.W;
-  for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-    const Seg sg = decode_seg(P, item);
-    const int col = sg.w0 - 4 + idx;
-    const bool ok = idx >= 4 && idx < 124 && col < P.W;
-    float* o = P.out + size_t(sg.n) * 3 * plane + size_t(sg.h0) * P.W + col;
-    for (int r = sg.h0; r < sg.h1; ++r, o += P.W) {
-      const int slot = r & 7;
-      dp.wait(accT_done, slot);
-      ptx::tc_fence_after_sync();
-      uint32_t v[4];
-      tmem_ld4(lb + 16u * uint32_t(slot), v);
-      ptx::tmem_wait_ld();
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&accT_free[slot]);
-      if (ok) {
-        const float f0 = __uint_as_float(v[0]) + b0, f1 = __uint_as_float(v[1]) + b1, f2 = __uint_as_float(v[2]) + b2;
-        o[0] = 1.0f / (1.0f + __expf(-f0));
-        o[plane] = 1.0f / (1.0f + __expf(-f1));
-        o[2 * plane] = 1.0f / (1.0f + __expf(-f2));
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ loader (F0 -> G0)
-__device__ __forceinline__ void loader(const FParams& P, const Smem& S, uint64_t* full, uint64_t* empty, int t, int lane) {
-  Ring gr;
-  ptx::mbar_wait(S.w_full, 0);
-  const uint4 sc0 = ptx::lds128(S.blob + kG0TabOff), sc1 = ptx::lds128(S.blob + kG0TabOff + 16u);
-  const uint4 sh0 = ptx::lds128(S.blob + kG0TabOff + 32u), sh1 = ptx::lds128(S.blob + kG0TabOff + 48u);
-  const __nv_bfloat162* sc[2] = {reinterpret_cast<const __nv_bfloat162*>(&sc0), reinterpret_cast<const __nv_bfloat162*>(&sc1)};
-  const __nv_bfloat162* sh[2] = {reinterpret_cast<const __nv_bfloat162*>(&sh0), reinterpret_cast<const __nv_bfloat162*>(&sh1)};
-  const uint32_t off[2] = {sw32_off(t, 0), sw32_off(t, 1)};
+// ------------------------------------------------------------------------------------------------ loader (F0 -> G0, TS)
+__device__ __forceinline__ void loader(const FParams& P, const Smem& S, int t, int lane) {
+  Ring gr, tsr;
+  ptx::mbar_wait_relaxed(S.w_full, 0);
+  const uint32_t off0 = sw32_off(t, 0), off1 = sw32_off(t, 1);
   const int IH = P.H >> 1, IW = P.W >> 1;
   const size_t plane = size_t(P.H) * P.W;
   for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
@@ -397,63 +492,106 @@ __device__ __forceinline__ void loader(const FParams& P, const Smem& S, uint64_t
     const float* xn = P.x + size_t(sg.n) * 3 * plane + col;
     for (int r = lo0; r < hi0; r += 2) {  // rows r (even) and r + 1 share the three half-resolution rows j-1, j, j+1
       const int j = r >> 1;
-      const int rows[3] = {max(j - 1, 0), j, min(j + 1, IH - 1)};
-      float tv[3][2][3];
+      const int jm = max(j - 1, 0), jp = min(j + 1, IH - 1);
+      // horizontally interpolated half-resolution rows (3 channels each), and the six x values of both output rows
+      float hz[3][3];
       float xv[2][3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) hz[a][ch] = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) xv[dy][ch] = 0.f;
       if (col_ok) {
-        uint2 raw[3][2];
+        uint2 q0[3], q1[3];
+        const int rws[3] = {jm, j, jp};
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          raw[a][0] = *reinterpret_cast<const uint2*>(tn + (size_t(rows[a]) * IW + c0) * P.t4_ld);
-          raw[a][1] = *reinterpret_cast<const uint2*>(tn + (size_t(rows[a]) * IW + c1) * P.t4_ld);
+          q0[a] = *reinterpret_cast<const uint2*>(tn + (size_t(rws[a]) * IW + c0) * P.t4_ld);
+          q1[a] = *reinterpret_cast<const uint2*>(tn + (size_t(rws[a]) * IW + c1) * P.t4_ld);
         }
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) xv[dy][ch] = xn[ch * plane + size_t(r + dy) * P.W];
 #pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            tv[a][b][0] = bflo(raw[a][b].x);
-            tv[a][b][1] = bfhi(raw[a][b].x);
-            tv[a][b][2] = bflo(raw[a][b].y);
-          }
+        for (int a = 0; a < 3; ++a) {
+          hz[a][0] = wx0 * bflo(q0[a].x) + wx1 * bflo(q1[a].x);
+          hz[a][1] = wx0 * bfhi(q0[a].x) + wx1 * bfhi(q1[a].x);
+          hz[a][2] = wx0 * bflo(q0[a].y) + wx1 * bflo(q1[a].y);
+        }
       }
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy) {
-        ptx::mbar_wait(&empty[gr.i], (gr.w & 1) ^ 1);
-        uint4 o[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+        const int row = r + dy;
+        const bool tsrow = row >= sg.h0 && row < sg.h1;
+        if (t == 0) {
+          bool ok = ptx::mbar_test_a(S.empty + 8u * uint32_t(gr.i), (gr.w & 1) ^ 1);
+          if (tsrow) ok &= ptx::mbar_test_a(S.ts_empty + 8u * uint32_t(tsr.i), (tsr.w & 1) ^ 1);
+          if (!ok) {
+            ptx::mbar_wait_a(S.empty + 8u * uint32_t(gr.i), (gr.w & 1) ^ 1);
+            if (tsrow) ptx::mbar_wait_a(S.ts_empty + 8u * uint32_t(tsr.i), (tsr.w & 1) ^ 1);
+          }
+        }
+        group_sync(5);
+        uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = make_uint4(0u, 0u, 0u, 0u);
+        float4 tsum = lds_f4(S.blob + kBiasOff + 4 * 64);  // transition bias
         if (col_ok) {
           const int r0 = dy ? 1 : 0, r1 = dy ? 2 : 1;
           const float wy0 = dy ? 0.75f : 0.25f, wy1 = dy ? 0.25f : 0.75f;
           __nv_bfloat16 f[3];
 #pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            const float up = wy0 * (wx0 * tv[r0][0][ch] + wx1 * tv[r0][1][ch]) + wy1 * (wx0 * tv[r1][0][ch] + wx1 * tv[r1][1][ch]);
-            f[ch] = __float2bfloat16_rn(up + xv[dy][ch]);
+          for (int ch = 0; ch < 3; ++ch) f[ch] = __float2bfloat16_rn((wy0 * hz[r0][ch] + wy1 * hz[r1][ch]) + xv[dy][ch]);
+          // K slot k = 3*layer + channel (k = 12..15 unused: scale = shift = 0); tables stay in shared memory
+          const uint4 sc0 = ptx::lds128(S.blob + kG0TabOff), sh0 = ptx::lds128(S.blob + kG0TabOff + 32u);
+          const uint4 sc1 = ptx::lds128(S.blob + kG0TabOff + 16u), sh1 = ptx::lds128(S.blob + kG0TabOff + 48u);
+          const __nv_bfloat162* c0p = reinterpret_cast<const __nv_bfloat162*>(&sc0);
+          const __nv_bfloat162* h0p = reinterpret_cast<const __nv_bfloat162*>(&sh0);
+          const __nv_bfloat162* c1p = reinterpret_cast<const __nv_bfloat162*>(&sc1);
+          const __nv_bfloat162* h1p = reinterpret_cast<const __nv_bfloat162*>(&sh1);
+          __nv_bfloat162* a0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+          __nv_bfloat162* a1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 rp;
+            rp.x = f[(2 * e) % 3];
+            rp.y = f[(2 * e + 1) % 3];
+            a0[e] = __hfma2_relu(rp, c0p[e], h0p[e]);
+            rp.x = f[(8 + 2 * e) % 3];
+            rp.y = f[(8 + 2 * e + 1) % 3];
+            a1[e] = __hfma2_relu(rp, c1p[e], h1p[e]);
           }
-          // K slot k = 3*consumer + channel (k = 15 unused: scale = shift = 0)
+          if (tsrow) {  // F0 term of the transition (physical channels 0..2)
+            const uint2 tsc = *reinterpret_cast<const uint2*>(__cvta_shared_to_generic(S.blob + kTActOff));
+            const uint2 tsh = *reinterpret_cast<const uint2*>(__cvta_shared_to_generic(S.blob + kTActOff + 160u));
+            __nv_bfloat162 p01, p2;
+            p01.x = f[0]; p01.y = f[1]; p2.x = f[2]; p2.y = f[2];
+            const __nv_bfloat162 a01 = __hfma2_relu(p01, *reinterpret_cast<const __nv_bfloat162*>(&tsc.x), *reinterpret_cast<const __nv_bfloat162*>(&tsh.x));
+            const __nv_bfloat162 a2 = __hfma2_relu(p2, *reinterpret_cast<const __nv_bfloat162*>(&tsc.y), *reinterpret_cast<const __nv_bfloat162*>(&tsh.y));
+            const float av[3] = {__low2float(a01), __high2float(a01), __low2float(a2)};
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&o[hf]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int k = 8 * hf + 2 * e;
-              __nv_bfloat162 rp;
-              rp.x = f[k % 3];
-              rp.y = f[(k + 1) % 3];
-              a[e] = __hfma2_relu(rp, sc[hf][e], sh[hf][e]);
-            }
+            const float4 wa = lds_f4(S.blob + kTWOff), wb = lds_f4(S.blob + kTWOff + 64u), wc = lds_f4(S.blob + kTWOff + 128u);
+            tsum.x = fmaf(wa.z, av[2], fmaf(wa.y, av[1], fmaf(wa.x, av[0], tsum.x)));
+            tsum.y = fmaf(wb.z, av[2], fmaf(wb.y, av[1], fmaf(wb.x, av[0], tsum.y)));
+            tsum.z = fmaf(wc.z, av[2], fmaf(wc.y, av[1], fmaf(wc.x, av[0], tsum.z)));
           }
         }
         const uint32_t base = S.rows + uint32_t(gr.i) * kRowBytes;
-        ptx::sts128(base + off[0], o[0]);
-        ptx::sts128(base + off[1], o[1]);
+        ptx::sts128(base + off0, o0);
+        ptx::sts128(base + off1, o1);
+        if (tsrow) ptx::sts128(S.ts + uint32_t(tsr.i) * kTsRowBytes + uint32_t(t) * 16u,
+                               make_uint4(__float_as_uint(tsum.x), __float_as_uint(tsum.y), __float_as_uint(tsum.z), 0u));
         ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&full[gr.i]);
+        group_sync(5);
+        if (t == 0) {
+          arrive_a(S.full + 8u * uint32_t(gr.i));
+          if (tsrow) arrive_a(S.ts_full + 8u * uint32_t(tsr.i));
+          FTRACE(12, row);
+        }
         gr.step(kG0Depth);
+        if (tsrow) tsr.step(kTsDepth);
       }
     }
   }
@@ -462,23 +600,21 @@ __device__ __forceinline__ void loader(const FParams& P, const Smem& S, uint64_t
 __global__ void __launch_bounds__(kThreads, 1) dense_fused_kernel(const FParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full[kRowSlots], empty[kRowSlots], acc_done[16], acc_free[16], accT_done[8], accT_free[8], w_full;
+  __shared__ uint64_t full[kRowSlots], empty[kRowSlots], acc_done[16], acc_free[16], ts_full[5 * kTsDepth], ts_empty[kTsDepth], w_full;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int i = 0; i < kRowSlots; ++i) {
-      ptx::mbar_init(&full[i], 4);
-      ptx::mbar_init(&empty[i], i < kG0Depth ? 5 : 1);
+      ptx::mbar_init(&full[i], 1);  // one arrival by the producing group's leader
+      ptx::mbar_init(&empty[i], i < kG0Depth ? 4 : 1);
     }
     for (int i = 0; i < 16; ++i) {
       ptx::mbar_init(&acc_done[i], 1);
-      ptx::mbar_init(&acc_free[i], 4);
+      ptx::mbar_init(&acc_free[i], 1);
     }
-    for (int i = 0; i < 8; ++i) {
-      ptx::mbar_init(&accT_done[i], 1);
-      ptx::mbar_init(&accT_free[i], 4);
-    }
+    for (int i = 0; i < 5 * kTsDepth; ++i) ptx::mbar_init(&ts_full[i], 1);
+    for (int i = 0; i < kTsDepth; ++i) ptx::mbar_init(&ts_empty[i], 1);
     ptx::mbar_init(&w_full, 1);
     ptx::fence_mbar_init();
   }
@@ -486,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_fused_kernel(const FParams 
     ptx::tmem_alloc(&tmem_base_s, 512);
     ptx::tmem_relinquish();
   }
-  {  // operand rows start as zeros (ring index 0 of groups 1-4 and the unused K slot are never written afterwards)
+  {  // operand rows start as zeros (ring index 0 of groups 1-3 and the unused K slots are never written afterwards)
     uint4* rows = reinterpret_cast<uint4*>(smem + kBlobPad);
     for (int i = tid; i < (kRowSlots * kRowBytes + 256) / 16; i += kThreads) rows[i] = make_uint4(0u, 0u, 0u, 0u);
   }
@@ -497,12 +633,13 @@ __global__ void __launch_bounds__(kThreads, 1) dense_fused_kernel(const FParams 
   Smem S;
   S.blob = ptx::smem_u32(smem);
   S.rows = S.blob + kBlobPad;
+  S.ts = S.blob + kTsOff;
   S.full = ptx::smem_u32(full);
   S.empty = ptx::smem_u32(empty);
   S.acc_done = ptx::smem_u32(acc_done);
   S.acc_free = ptx::smem_u32(acc_free);
-  S.accT_done = ptx::smem_u32(accT_done);
-  S.accT_free = ptx::smem_u32(accT_free);
+  S.ts_full = ptx::smem_u32(ts_full);
+  S.ts_empty = ptx::smem_u32(ts_empty);
   S.w_full = &w_full;
   S.tmem = tmem_base_s;
   if (warp == 0 && ptx::elect_one()) {
@@ -519,17 +656,9 @@ __global__ void __launch_bounds__(kThreads, 1) dense_fused_kernel(const FParams 
   __syncthreads();
   ptx::tc_fence_after_sync();
 
-  if (warp == 0) issuer_layer<0>(P, S, lane);
-  else if (warp == 1) issuer_layer<1>(P, S, lane);
-  else if (warp == 2) issuer_layer<2>(P, S, lane);
-  else if (warp == 3) issuer_layer<3>(P, S, lane);
-  else if (warp < 8) loader(P, S, full, empty, (warp - 4) * 32 + lane, lane);
-  else if (warp < 12) epilogue_layer<0>(P, S, full, empty, acc_done + 0, acc_free + 0, warp & 3, lane);
-  else if (warp < 16) epilogue_layer<1>(P, S, full, empty, acc_done + 4, acc_free + 4, warp & 3, lane);
-  else if (warp < 20) epilogue_layer<2>(P, S, full, empty, acc_done + 8, acc_free + 8, warp & 3, lane);
-  else if (warp < 24) epilogue_layer<3>(P, S, full, empty, acc_done + 12, acc_free + 12, warp & 3, lane);
-  else if (warp < 28) epilogue_transition(P, S, accT_done, accT_free, warp & 3, lane);
-  else issuer_transition(P, S, lane);
+  if (warp < 4) issuer_layer(P, S, warp, lane);
+  else if (warp < 8) loader(P, S, (warp - 4) * 32 + lane, lane);
+  else epilogue_layer(P, S, (warp - 8) >> 2, warp & 3, lane);
 
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -569,31 +698,32 @@ int fused_fd_pack_create(const FusedFdLayer layers[5], FusedFdPack** out) {
             }
           }
       }
-  for (int g = 0; g < 5; ++g) {
-    uint8_t* blk = blob.data() + kWTOff + g * 512;
-    for (int co = 0; co < 16; ++co) {
-      if (g == 0) {
-        for (int ch = 0; ch < 3; ++ch) put_sw32(blk, co, 12 + ch, wat(layers[4], 0, ch, co));
-      } else {
-        for (int k = 0; k < 16; ++k) put_sw32(blk, co, k, wat(layers[4], 0, 16 * g + k, co));
-      }
-    }
-  }
   auto put_b = [&](int off, float v) {
     const bf16 b = __float2bfloat16_rn(v);
     std::memcpy(blob.data() + off, &b, 2);
   };
-  for (int cp = 1; cp <= 4; ++cp)
+  for (int cp = 1; cp <= 3; ++cp)
     for (int g = 1; g <= cp; ++g)
       for (int k = 0; k < 16; ++k) {
+        // group g = output of layer g-1: its bias is folded into the shift, relu(s*(v+b)+t) = relu(s*v + (s*b+t))
         put_b(kTabOff + ring_id(cp, g) * 64 + k * 2, layers[cp].pre_s[16 * g + k]);
-        put_b(kTabOff + ring_id(cp, g) * 64 + 32 + k * 2, layers[cp].pre_t[16 * g + k]);
+        put_b(kTabOff + ring_id(cp, g) * 64 + 32 + k * 2, layers[cp].pre_s[16 * g + k] * layers[g - 1].bias[k] + layers[cp].pre_t[16 * g + k]);
       }
-  for (int cp = 0; cp <= 4; ++cp)
+  for (int cp = 0; cp <= 3; ++cp)
     for (int ch = 0; ch < 3; ++ch) {
       put_b(kG0TabOff + (3 * cp + ch) * 2, layers[cp].pre_s[ch]);
       put_b(kG0TabOff + 32 + (3 * cp + ch) * 2, layers[cp].pre_t[ch]);
     }
+  // transition (1x1, 80 physical input channels -> 3): pre-activation tables (bf16) and weights as fp32 values of their
+  // bf16 roundings (the products with bf16 activations are then exact in fp32, as on the tensor-core path)
+  for (int ci = 0; ci < 80; ++ci) {
+    put_b(kTActOff + ci * 2, layers[4].pre_s[ci]);
+    put_b(kTActOff + 160 + ci * 2, ci < 16 ? layers[4].pre_t[ci] : layers[4].pre_s[ci] * layers[ci / 16 - 1].bias[ci % 16] + layers[4].pre_t[ci]);
+    for (int co = 0; co < 3; ++co) {
+      const float v = __bfloat162float(__float2bfloat16_rn(wat(layers[4], 0, ci, co)));
+      std::memcpy(blob.data() + kTWOff + ((ci / 16) * 3 + co) * 64 + (ci % 16) * 4, &v, 4);
+    }
+  }
   for (int c = 0; c < 5; ++c)
     for (int co = 0; co < 16; ++co) {
       const float v = layers[c].bias[co];
@@ -643,8 +773,30 @@ int fused_fd_launch(const FusedFdPack& pk, const void* t4, int t4_ld, const floa
   }
   P.nitems = N * P.strips * P.segs;
   CDAN_CUDA_OK(cudaFuncSetAttribute(dense_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  static const bool tracing = getenv("CDAN_FUSED_TRACE") && atoi(getenv("CDAN_FUSED_TRACE")) != 0;
+  static unsigned long long* d_trace = nullptr;
+  if (tracing) {
+    if (!d_trace) cudaMalloc(&d_trace, kTraceRoles * kTraceRows * sizeof(unsigned long long));
+    cudaMemsetAsync(d_trace, 0, kTraceRoles * kTraceRows * sizeof(unsigned long long), stream);
+    P.trace = d_trace;
+  }
   dense_fused_kernel<<<std::min(P.nitems, sms), kThreads, kSmemBytes, stream>>>(P);
   CDAN_CUDA_OK(cudaGetLastError());
+  if (tracing) {
+    cudaStreamSynchronize(stream);
+    std::vector<unsigned long long> t(kTraceRoles * kTraceRows);
+    cudaMemcpy(t.data(), d_trace, t.size() * 8, cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    for (auto v : t) if (v && v < t0) t0 = v;
+    fprintf(stderr, "FUSED TRACE N=%d H=%d W=%d SEG=%d segs=%d strips=%d items=%d\n", N, H, W, P.SEG, P.segs, P.strips, P.nitems);
+    const char* names[kTraceRoles] = {"L0_issued", "L1_issued", "L2_issued", "L3_issued", "E0_start", "E1_start", "E2_start", "E3_start",
+                                      "E0_done", "E1_done", "E2_done", "E3_done", "loader", "E0_accfree", "E0_versions", "E0_tsterm", "E0_tsupd", "", "", ""};
+    for (int r = 0; r < 17; ++r) {
+      fprintf(stderr, "%-10s", names[r]);
+      for (int i = 0; i < kTraceRows; ++i) fprintf(stderr, " %7lld", t[r * kTraceRows + i] ? (long long)(t[r * kTraceRows + i] - t0) : -1ll);
+      fprintf(stderr, "\n");
+    }
+  }
   return 0;
 }
 

@@ -66,6 +66,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking phase test.  mbarrier.try_wait with a suspend-time hint compiles to a loop that SLEEPS FIRST (NANOSLEEP.SYNCS,
+// woken by the next barrier event on the SM or the time-out) and only then checks the phase, so waiting on a phase that has
+// already completed still costs 300-500 cycles (measured per wait in conv_stream2 and dense_fused traces).  test_wait is a
+// single SYNCS.PHASECHK: every wait below tries it once before entering the blocking loop.
+__device__ __forceinline__ bool mbar_test_a(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded waits: a protocol bug must fail loudly (trap -> launch failure), never hang the GPU.
 // mbar_wait        : tight poll — for the latency-critical MMA issuer (one warp).
 // mbar_wait_relaxed: poll with nanosleep back-off — for producer / epilogue warps, so that their polling does not
@@ -86,6 +101,7 @@ static __device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity)
 // about ten times per wait on B200, and the compiler-generated C++ loop cost ~16 issue slots per wake-up — a third of
 // all instructions the streaming convolution executed.  Still bounded: after CDAN_MBAR_MAX_POLLS failed polls it traps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_test_a(smem_u32(bar), parity)) return;
   uint32_t timed_out;
   asm volatile(
       "{\n\t"
@@ -110,6 +126,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Same with the barrier given as a 32-bit shared-window address: hot single-thread roles (MMA issuers) convert their
 // barrier arrays once — the generic->shared conversion (S2R + LEA) otherwise sits on the dependency chain of every wait.
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {
+  if (mbar_test_a(bar_addr, parity)) return;
   uint32_t timed_out;
   asm volatile(
       "{\n\t"
@@ -131,10 +148,38 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) 
       : "memory");
   if (timed_out) mbar_timeout(nullptr, parity | (bar_addr << 1));
 }
+// Bounded wait with nanosleep back-off between polls.  try_wait returns after a short, implementation-defined time when
+// the phase is still pending; a kernel in which twenty warps wait at any moment (dense_fused.cu) otherwise spends most
+// of its issue slots in poll loops (ncu: 61 % issue-active, 16 % of all instructions branches) and starves the few warps
+// that have work.
+__device__ __forceinline__ void mbar_wait_sleep_a(uint32_t bar_addr, uint32_t parity, uint32_t sleep_ns) {
+  uint32_t timed_out;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .u32 cnt;\n\t"
+      "mov.u32 cnt, 0;\n\t"
+      "mov.u32 %0, 0;\n"
+      "CDAN_WAITS_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "@p bra CDAN_WAITS_DONE;\n\t"
+      "nanosleep.u32 %5;\n\t"
+      "add.u32 cnt, cnt, 1;\n\t"
+      "setp.lt.u32 p, cnt, %4;\n\t"
+      "@p bra CDAN_WAITS_LOOP;\n\t"
+      "mov.u32 %0, 1;\n"
+      "CDAN_WAITS_DONE:\n\t"
+      "}"
+      : "=r"(timed_out)
+      : "r"(bar_addr), "r"(parity), "r"(CDAN_MBAR_SUSPEND_NS), "r"(CDAN_MBAR_MAX_POLLS), "r"(sleep_ns)
+      : "memory");
+  if (timed_out) mbar_timeout(nullptr, parity | (bar_addr << 1));
+}
 __device__ __forceinline__ void umma_commit_a(uint32_t bar_addr) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns = 64) {
+  if (mbar_test_a(smem_u32(bar), parity)) return;
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
     __nanosleep(sleep_ns);

@@ -1,8 +1,10 @@
 """The fused final dense block (csrc/dense_fused.cu: bilinear x2 + x, four 3x3 growth layers, 1x1 transition, sigmoid in
 ONE kernel) against (a) the CPU reference / oracle and (b) the layer-by-layer path of the same library (plan option
-"fd_fused" = 0).  (b) is not bitwise: both paths round the same intermediate values to bf16 at the same points, but the
-fp32 association of the three vertical-tap partial sums differs with the accumulator ring size, so single bf16 roundings
-can flip; the stated bound is 4e-3 max abs / 2e-4 mean abs on outputs in (0,1).  Geometry cases: widths that are not a
+"fd_fused" = 0).  (b) is not bitwise: the layer-wise path stores bf16(conv + bias) and activates that, the fused kernel
+rounds the accumulator to bf16 and folds the bias into the activation shift (relu(s*(v+b)+t) = relu(s*v + (s*b+t))), and the
+fp32 association of the three vertical-tap partial sums differs with the accumulator ring size — two independent bf16
+rounding patterns of the same quantity.  Stated bound between the two: 3e-2 max abs / 2e-3 mean abs on outputs in (0,1) (measured: up to 1.7e-2 / 1.0e-3, i.e. well inside either path's own distance from the fp32 oracle, 2e-2..8e-2 max);
+against the oracle the fused path must be as close as the layer-wise one (mean abs error within 1.25x, max within 1.5x).  Geometry cases: widths that are not a
 multiple of the 120-column strip, one-strip images, heights down to 8 rows, multi-segment strips, batches."""
 import pytest
 import torch
@@ -41,10 +43,13 @@ def test_fused_final_dense_vs_layerwise_and_oracle(cuda_device, shape):
     assert n_layer - n_fused == 5                      # up_add_input + 4 layers + transition -> one launch
     assert torch.equal(y_fused, y_again)               # deterministic, and switching the option back and forth is clean
     d = (y_fused - y_layer).abs()
-    assert float(d.max()) < 4e-3 and float(d.mean()) < 2e-4, (float(d.max()), float(d.mean()))
     ref = O.cdan_forward(sd, x)
     e_f, e_l = float((y_fused - ref).abs().max()), float((y_layer - ref).abs().max())
-    assert e_f < 0.1 and e_f < 1.5 * e_l + 5e-3, (e_f, e_l)  # as close to the oracle as the layer-wise bf16 path
+    m_f, m_l = float((y_fused - ref).abs().mean()), float((y_layer - ref).abs().mean())
+    print(f"fused vs layer-wise: max {float(d.max()):.2e} mean {float(d.mean()):.2e}; vs oracle: fused max {e_f:.2e} mean {m_f:.2e}, "
+          f"layer-wise max {e_l:.2e} mean {m_l:.2e}")
+    assert float(d.max()) < 3e-2 and float(d.mean()) < 2e-3, (float(d.max()), float(d.mean()))
+    assert e_f < 0.1 and e_f < 1.5 * e_l + 2e-3 and m_f < 1.25 * m_l + 1e-4, (e_f, e_l, m_f, m_l)
 
 
 def test_fused_final_dense_segments_and_batch_independence(cuda_device):
@@ -63,4 +68,4 @@ def test_fused_final_dense_segments_and_batch_independence(cuda_device):
         plan.set_option("fd_fused", 1)
     assert torch.equal(y, singles)
     row_err = (y - y_layer).abs().amax(dim=(0, 1, 3))
-    assert float(row_err.max()) < 4e-3, int(row_err.argmax())
+    assert float(row_err.max()) < 3e-2 and float(row_err.mean()) < 6e-3, (int(row_err.argmax()), float(row_err.max()))
