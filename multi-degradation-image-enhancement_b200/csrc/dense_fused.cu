@@ -137,15 +137,24 @@ __device__ __forceinline__ uint32_t sw32_off(int idx, int half) { return uint32_
 __device__ __forceinline__ void arrive_a(uint32_t bar_addr) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar_addr) : "memory");
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   const uint4 u = ptx::lds128(addr);
   return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
 }
 
+// Blocking wait, out of line: the hot loops only carry the non-blocking tests (the kernel is sensitive to the size of its
+// instruction streams — 24 warps at different program counters share the SM's instruction caches).
+static __device__ __noinline__ void wait_slow(uint32_t bar_addr, uint32_t parity) { ptx::mbar_wait_a(bar_addr, parity); }
+
 // One lane polls, the warp follows: a warp-wide mbarrier.try_wait costs every lane a trip through the barrier unit
 // (~400 cycles per already-completed wait measured in the first version of this kernel).
 __device__ __forceinline__ void wait_l0(uint32_t bar_addr, uint32_t parity, int lane) {
-  if (lane == 0) ptx::mbar_wait_a(bar_addr, parity);
+  if (lane == 0 && !ptx::mbar_test_a(bar_addr, parity)) wait_slow(bar_addr, parity);
   __syncwarp();
 }
 
@@ -155,7 +164,7 @@ __device__ __forceinline__ void wait_l0(uint32_t bar_addr, uint32_t parity, int 
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 struct Smem {
-  uint32_t blob, rows, ts, full, empty, acc_done, acc_free, ts_full, ts_empty;  // shared-window addresses
+  uint32_t blob, rows, ts, full, empty, acc_done, acc_free, ts_full, ts_empty, gconst;  // shared-window addresses
   uint64_t* w_full;
   uint32_t tmem;
 };
@@ -165,7 +174,7 @@ struct Smem {
 // SlotPhases::claim_a with the poll done by lane 0 only
 __device__ __forceinline__ void claim_l0(SlotPhases& fp, uint32_t free_bars, int s, int lane) {
   if ((fp.used >> s) & 1u) {
-    if (lane == 0) ptx::mbar_wait_a(free_bars + 8u * uint32_t(s), (fp.par >> s) & 1u);
+    if (lane == 0 && !ptx::mbar_test_a(free_bars + 8u * uint32_t(s), (fp.par >> s) & 1u)) wait_slow(free_bars + 8u * uint32_t(s), (fp.par >> s) & 1u);
     fp.par ^= 1u << s;
   }
   fp.used |= 1u << s;
@@ -212,11 +221,11 @@ __device__ __forceinline__ void issuer_layer(const FParams& P, const Smem& S, co
           for (int g = 1; g <= 3; ++g)
             if (g <= C) ok &= ptx::mbar_test_a(S.full + 8u * uint32_t(ring_base_fast(C, g) + vr[g - 1].i), vr[g - 1].w & 1);
           if (!ok) {
-            if (need_claim) ptx::mbar_wait_a(acc_free + 8u * uint32_t(sn), (fp.par >> sn) & 1u);
-            ptx::mbar_wait_a(S.full + 8u * uint32_t(g0.i), g0.w & 1);
+            if (need_claim) wait_slow(acc_free + 8u * uint32_t(sn), (fp.par >> sn) & 1u);
+            wait_slow(S.full + 8u * uint32_t(g0.i), g0.w & 1);
 #pragma unroll
             for (int g = 1; g <= 3; ++g)
-              if (g <= C) ptx::mbar_wait_a(S.full + 8u * uint32_t(ring_base_fast(C, g) + vr[g - 1].i), vr[g - 1].w & 1);
+              if (g <= C) wait_slow(S.full + 8u * uint32_t(ring_base_fast(C, g) + vr[g - 1].i), vr[g - 1].w & 1);
           }
         }
         if (need_claim) fp.par ^= 1u << sn;
@@ -292,9 +301,11 @@ __device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, 
   const int bar_id = 1 + C;
   const bool leader = q == C && lane == 0;  // the groups' leaders sit on different SM sub-partitions
   const uint32_t acc_free = S.acc_free + 32u * C, acc_done = S.acc_done + 32u * C;
-  // consumer k of this layer's group: layer cp = C + 1 + k reads it through ring (cp, G)
-  auto rbk = [&](int k) { return ring_base_fast(C + 1 + k, G); };
-  auto tabk = [&](int k) { return S.blob + kTabOff + uint32_t(ring_id(C + 1 + k, G)) * 64u; };
+  // consumer k of this layer's group: layer cp = C + 1 + k reads it through ring (cp, G); base slot and activation-table
+  // address come from a small shared-memory table (one LDS with an immediate offset instead of a select chain per use)
+  const uint32_t gc = S.gconst + uint32_t(C) * 32u;
+  auto rbk = [&](int k) { return int(lds32(gc + 4u * k)); };
+  auto tabk = [&](int k) { return lds32(gc + 12u + 4u * k); };
   Ring cr[3];
   Ring tsr;  // transition partial-sum ring position (rows [h0, h1) of every item, in order)
   uint32_t dpar = 0;  // acc_done phase parity per slot
@@ -332,11 +343,11 @@ __device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, 
           if (take[k]) ok &= ptx::mbar_test_a(S.empty + 8u * uint32_t(rbk(k) + cr[k].i), (cr[k].w & 1) ^ 1);
         if (tsrow) ok &= ptx::mbar_test_a(ts_in + 8u * uint32_t(tsr.i), tsr.w & 1);
         if (!ok) {
-          ptx::mbar_wait_a(acc_done + 8u * uint32_t(slot), (dpar >> slot) & 1u);
+          wait_slow(acc_done + 8u * uint32_t(slot), (dpar >> slot) & 1u);
 #pragma unroll
           for (int k = 0; k < 3; ++k)
-            if (take[k]) ptx::mbar_wait_a(S.empty + 8u * uint32_t(rbk(k) + cr[k].i), (cr[k].w & 1) ^ 1);
-          if (tsrow) ptx::mbar_wait_a(ts_in + 8u * uint32_t(tsr.i), tsr.w & 1);
+            if (take[k]) wait_slow(S.empty + 8u * uint32_t(rbk(k) + cr[k].i), (cr[k].w & 1) ^ 1);
+          if (tsrow) wait_slow(ts_in + 8u * uint32_t(tsr.i), tsr.w & 1);
         }
       }
       dpar ^= 1u << slot;
@@ -531,8 +542,8 @@ __device__ __forceinline__ void loader(const FParams& P, const Smem& S, int t, i
           bool ok = ptx::mbar_test_a(S.empty + 8u * uint32_t(gr.i), (gr.w & 1) ^ 1);
           if (tsrow) ok &= ptx::mbar_test_a(S.ts_empty + 8u * uint32_t(tsr.i), (tsr.w & 1) ^ 1);
           if (!ok) {
-            ptx::mbar_wait_a(S.empty + 8u * uint32_t(gr.i), (gr.w & 1) ^ 1);
-            if (tsrow) ptx::mbar_wait_a(S.ts_empty + 8u * uint32_t(tsr.i), (tsr.w & 1) ^ 1);
+            wait_slow(S.empty + 8u * uint32_t(gr.i), (gr.w & 1) ^ 1);
+            if (tsrow) wait_slow(S.ts_empty + 8u * uint32_t(tsr.i), (tsr.w & 1) ^ 1);
           }
         }
         group_sync(5);
@@ -602,8 +613,14 @@ __global__ void __launch_bounds__(kThreads, 1) dense_fused_kernel(const FParams 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full[kRowSlots], empty[kRowSlots], acc_done[16], acc_free[16], ts_full[5 * kTsDepth], ts_empty[kTsDepth], w_full;
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t gconst[4 * 8];  // per epilogue group: ring base slot of consumer k = 0..2, activation-table address of k = 0..2
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  if (tid < 12) {
+    const int c = tid / 3, k = tid % 3, cp = min(c + 1 + k, 3), g = min(c + 1, cp);
+    gconst[c * 8 + k] = uint32_t(ring_base_fast(cp, g));
+    gconst[c * 8 + 3 + k] = ptx::smem_u32(smem) + kTabOff + uint32_t(ring_id(cp, g)) * 64u;
+  }
   if (tid == 0) {
     for (int i = 0; i < kRowSlots; ++i) {
       ptx::mbar_init(&full[i], 1);  // one arrival by the producing group's leader
@@ -640,6 +657,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_fused_kernel(const FParams 
   S.acc_free = ptx::smem_u32(acc_free);
   S.ts_full = ptx::smem_u32(ts_full);
   S.ts_empty = ptx::smem_u32(ts_empty);
+  S.gconst = ptx::smem_u32(gconst);
   S.w_full = &w_full;
   S.tmem = tmem_base_s;
   if (warp == 0 && ptx::elect_one()) {
