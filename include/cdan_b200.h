@@ -71,6 +71,32 @@ CDAN_API int cdan_forward_host(cdan_plan* plan, const float* x_host, float* y_ho
  * (x = u8 * float32(1/255)), run through cdan_forward and are quantised on the device exactly as cdan_quantize_u8. */
 CDAN_API int cdan_forward_host_u8(cdan_plan* plan, const unsigned char* x_host, unsigned char* y_host, int N, int H, int W);
 
+/* ---- spatial row tiling of very large images (BASELINE config C5: one 4K image over the GPUs of a box; the cross-row operators
+ *      are the 3x3 (transposed) convolutions, bilinear x2 and SpatialGate 7x7 of reference models/cdan.py:70-159, models/cbam.py:72-82,
+ *      the global pooling of ChannelGate is models/cbam.py:41,44).  One plan per band; band r of `nbands` owns the rows
+ *      cdan_band_rows reports (boundaries at multiples of 8 rows) and computes on them plus `halo` rows above and below
+ *      (multiple of 8, >= 24).  Halo rows of intermediate tensors are refreshed from the neighbouring bands only where the
+ *      schedule needs it (7 exchanges per forward at halo 24); ChannelGate statistics are all-reduced (SUM, MAX).
+ *      Transports: NCCL (one process per GPU, ncclSend/ncclRecv/ncclAllReduce on the caller's stream; libnccl.so.2 is loaded
+ *      at run time) or in-process (all bands in one process, one host thread per band calling cdan_forward_band
+ *      concurrently; used to test the schedule on a single GPU). */
+typedef struct cdan_band_group cdan_band_group;
+CDAN_API int cdan_band_group_create(int nbands, cdan_band_group** group_out);
+CDAN_API int cdan_band_group_destroy(cdan_band_group* group);
+CDAN_API int cdan_plan_band_attach_local(cdan_plan* plan, cdan_band_group* group, int rank);
+/* 128-byte NCCL unique id: create on rank 0, distribute with any host mechanism, pass to every rank's attach. */
+CDAN_API int cdan_band_nccl_unique_id(void* id_out, size_t len);
+CDAN_API int cdan_plan_band_attach_nccl(cdan_plan* plan, int rank, int nranks, const void* id, size_t len);
+CDAN_API int cdan_plan_band_detach(cdan_plan* plan);
+/* rows_out = {owned begin, owned end, extended begin, extended end} of band `rank` (rows of the full image). */
+CDAN_API int cdan_band_rows(int H, int nbands, int rank, int halo, int rows_out[4]);
+/* Forward of this plan's band.  x_ext / y_ext: fp32 NCHW [N,3,Hext,W] holding rows [extended begin, extended end) of the
+ * [N,3,H,W] image; on return the OWNED rows of y_ext equal the untiled forward's (halo rows of y_ext are scratch).
+ * All bands must make the call (collective). */
+CDAN_API int cdan_forward_band(cdan_plan* plan, void* stream, const float* x_ext, float* y_ext, int N, int H, int W, int halo);
+/* Counters of the most recent cdan_forward_band: {halo exchanges, halo bytes received, all-reduces}. */
+CDAN_API int cdan_band_stats(cdan_plan* plan, long long out[3]);
+
 /* Read an intermediate tensor of the most recent cdan_forward as fp32 NCHW (per-stage parity tests).
  * Names: "enc.out1","enc.out2","enc.out3" (max-pooled ConvBlock outputs = skip connections), "enc.dense1".."enc.dense3",
  * "enc.conv4","bottleneck","dec.bn1".."dec.bn4" (relu(bn(convT))), "dec.gated1".."dec.gated3" (cbam_i(.)*dense),

@@ -32,6 +32,15 @@ _PROTOTYPES = {
     "cdan_forward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
     "cdan_forward_host": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
     "cdan_forward_host_u8": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int]),
+    "cdan_band_group_create": (_c_int, [_c_int, ctypes.POINTER(_c_void_p)]),
+    "cdan_band_group_destroy": (_c_int, [_c_void_p]),
+    "cdan_plan_band_attach_local": (_c_int, [_c_void_p, _c_void_p, _c_int]),
+    "cdan_band_nccl_unique_id": (_c_int, [_c_void_p, ctypes.c_size_t]),
+    "cdan_plan_band_attach_nccl": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, ctypes.c_size_t]),
+    "cdan_plan_band_detach": (_c_int, [_c_void_p]),
+    "cdan_band_rows": (_c_int, [_c_int, _c_int, _c_int, _c_int, ctypes.POINTER(_c_int)]),
+    "cdan_forward_band": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int]),
+    "cdan_band_stats": (_c_int, [_c_void_p, ctypes.POINTER(ctypes.c_longlong)]),
     "cdan_stage_read": (_c_int, [_c_void_p, _c_void_p, _c_char_p, _c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "cdan_last_launch_count": (_c_int, [_c_void_p]),
     "cdan_profile_read": (_c_int, [_c_void_p, ctypes.c_char_p, ctypes.c_size_t]),
@@ -170,6 +179,36 @@ class Plan:
         _check(lib().cdan_forward_host_u8(self._h, _ptr(x_host), _ptr(y), n, h, w), "forward_host_u8")
         return y
 
+    # ---- spatial row tiling (include/cdan_b200.h "spatial row tiling"; host side in spatial_tiling.py)
+    def band_attach_local(self, group: "BandGroup", rank: int) -> None:
+        _check(lib().cdan_plan_band_attach_local(self._h, group._h, int(rank)), "plan_band_attach_local")
+        self._band_group = group  # keep the transport alive as long as the plan uses it
+
+    def band_attach_nccl(self, rank: int, nranks: int, unique_id: bytes) -> None:
+        buf = ctypes.create_string_buffer(bytes(unique_id), len(unique_id))
+        with torch.cuda.device(self.device):
+            _check(lib().cdan_plan_band_attach_nccl(self._h, int(rank), int(nranks), buf, len(unique_id)), "plan_band_attach_nccl")
+
+    def band_detach(self) -> None:
+        lib().cdan_plan_band_detach(self._h)
+        self._band_group = None
+
+    def forward_band(self, x_ext: torch.Tensor, height: int, halo: int, out: Optional[torch.Tensor] = None,
+                     stream: Optional[int] = None) -> torch.Tensor:
+        """x_ext: rows [extended begin, extended end) of the [N,3,height,W] image (band_rows); collective over the bands."""
+        if x_ext.dim() != 4 or x_ext.shape[1] != 3 or x_ext.device != self.device or x_ext.dtype != torch.float32 or not x_ext.is_contiguous():
+            raise RuntimeError("cdan_b200: forward_band needs a contiguous fp32 [N,3,Hext,W] tensor on the plan's device")
+        y = out if out is not None else torch.empty_like(x_ext)
+        n, _, _, w = x_ext.shape
+        st = _stream(self.device) if stream is None else stream
+        _check(lib().cdan_forward_band(self._h, _c_void_p(st), _ptr(x_ext), _ptr(y), n, int(height), w, int(halo)), "forward_band")
+        return y
+
+    def band_stats(self) -> Dict[str, int]:
+        out = (ctypes.c_longlong * 3)()
+        _check(lib().cdan_band_stats(self._h, out), "band_stats")
+        return {"halo_exchanges": int(out[0]), "halo_bytes_received": int(out[1]), "allreduces": int(out[2])}
+
     def stage(self, name: str) -> torch.Tensor:
         shape = (ctypes.c_int64 * 4)()
         s = _c_void_p(_stream(self.device))
@@ -191,6 +230,33 @@ class Plan:
     @property
     def last_launch_count(self) -> int:
         return lib().cdan_last_launch_count(self._h)
+
+
+class BandGroup:
+    """In-process transport between the bands of one process (one host thread per band drives its plan)."""
+
+    def __init__(self, nbands: int):
+        self._h = ctypes.c_void_p()
+        self.nbands = int(nbands)
+        _check(lib().cdan_band_group_create(self.nbands, ctypes.byref(self._h)), "band_group_create")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            lib().cdan_band_group_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+
+def band_rows(height: int, nbands: int, rank: int, halo: int) -> Tuple[int, int, int, int]:
+    """(owned begin, owned end, extended begin, extended end) — the library's band split (cdan_band_rows)."""
+    out = (_c_int * 4)()
+    _check(lib().cdan_band_rows(int(height), int(nbands), int(rank), int(halo), out), "band_rows")
+    return tuple(int(v) for v in out)
+
+
+def nccl_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(128)
+    _check(lib().cdan_band_nccl_unique_id(buf, 128), "band_nccl_unique_id")
+    return buf.raw
 
 
 # ------------------------------------------------------------------------------------------------ single operators

@@ -4,7 +4,7 @@ set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr"
-SRCS="plan.cu ops.cu conv_simt.cu conv_umma.cu conv_stream.cu dense_fused.cu cbam.cu glue.cu postproc.cu"
+SRCS="plan.cu ops.cu conv_simt.cu conv_umma.cu conv_stream.cu dense_fused.cu cbam.cu glue.cu postproc.cu band.cu"
 mkdir -p build
 OBJS=""
 PIDS=""

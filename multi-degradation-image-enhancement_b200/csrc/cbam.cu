@@ -10,6 +10,7 @@
 // exceed the L2, and a per-strip streaming version is latency-bound between its block barriers.)
 #include <algorithm>
 
+#include "band.cuh"
 #include "kernels.cuh"
 
 namespace cdan {
@@ -18,7 +19,7 @@ namespace {
 
 template <typename T>
 __global__ void __launch_bounds__(256) pool_partial_kernel(const T* __restrict__ x, int ld, int C, int HW, int W, int nblk,
-                                                            float* __restrict__ psum, float* __restrict__ pmax) {
+                                                            float* __restrict__ psum, float* __restrict__ pmax, size_t img_pixels) {
   extern __shared__ float red[];  // [npl][C] sums then [npl][C] maxes
   const int vecs = C >> 3;
   const int npl = 256 / vecs;  // pixel lanes
@@ -30,7 +31,7 @@ __global__ void __launch_bounds__(256) pool_partial_kernel(const T* __restrict__
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; m[j] = -INFINITY; }
   if (pl < npl) {
-    const T* base = x + size_t(n) * HW * ld + vc * 8;
+    const T* base = x + size_t(n) * img_pixels * ld + vc * 8;  // HW = pixels pooled (a row range in band mode)
     for (int p = p0 + pl; p < p1; p += npl) {
       const F8 v = load8<T>(base + size_t(p) * ld);
 #pragma unroll
@@ -50,6 +51,21 @@ __global__ void __launch_bounds__(256) pool_partial_kernel(const T* __restrict__
     }
     psum[(size_t(n) * nblk + blk) * C + c] = ss;
     pmax[(size_t(n) * nblk + blk) * C + c] = mm;
+  }
+}
+
+// Band mode: finish the reduction over this band's partials -> pooled sums [N][C] | maxima [N][C] (then all-reduced).
+__global__ void __launch_bounds__(256) pool_finish_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, int nblk,
+                                                           int C, int N, float* __restrict__ pooled) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float ss = 0.f, mm = -INFINITY;
+    for (int b = 0; b < nblk; ++b) {
+      ss += psum[(size_t(n) * nblk + b) * C + c];
+      mm = fmaxf(mm, pmax[(size_t(n) * nblk + b) * C + c]);
+    }
+    pooled[size_t(n) * C + c] = ss;
+    pooled[size_t(N + n) * C + c] = mm;
   }
 }
 
@@ -279,18 +295,32 @@ inline int grid_for(size_t total, int block = 256, int cap = 148 * 16) {
 
 template <typename T>
 int cbam_typed(const void* x, int x_ld, const void* mul, int mul_ld, void* out, int out_ld, int N, int H, int W, int C,
-               const CbamWeights& wt, const CbamScratch& sc, bool pooled, cudaStream_t s) {
+               const CbamWeights& wt, const CbamScratch& sc, bool pooled, cudaStream_t s, const CbamBand* band) {
   const int HW = H * W;
   const int vecs = C / 8;
   const int npl = 256 / vecs;
-  if (!pooled) {
-    pool_partial_kernel<T><<<dim3(sc.nblk, N), 256, 2 * npl * C * sizeof(float), s>>>((const T*)x, x_ld, C, HW, W, sc.nblk,
-                                                                                    sc.psum, sc.pmax);
+  if (band) {
+    // statistics of the owned rows only (the partials a fused producer wrote cover halo rows too and are not used)
+    const int nblk = cbam_pool_blocks(band->rows);
+    pool_partial_kernel<T><<<dim3(nblk, N), 256, 2 * npl * C * sizeof(float), s>>>(
+        (const T*)x + size_t(band->row0) * W * x_ld, x_ld, C, band->rows * W, W, nblk, sc.psum, sc.pmax, size_t(HW));
+    CDAN_CUDA_OK(cudaGetLastError());
+    pool_finish_kernel<<<N, 256, 0, s>>>(sc.psum, sc.pmax, nblk, C, N, sc.pooled);
+    CDAN_CUDA_OK(cudaGetLastError());
+    CDAN_TRY(band->comm->allreduce_sum_max(sc.pooled, sc.pooled + size_t(N) * C, N * C, s));
+    gate_mlp_kernel<<<N, 256, (2 * C + 2 * (C / 16)) * sizeof(float), s>>>(sc.pooled, sc.pooled + size_t(N) * C, 1, C, band->HW_full,
+                                                                           wt.w1, wt.b1, wt.w2, wt.b2, sc.gate);
+    CDAN_CUDA_OK(cudaGetLastError());
+  } else {
+    if (!pooled) {
+      pool_partial_kernel<T><<<dim3(sc.nblk, N), 256, 2 * npl * C * sizeof(float), s>>>((const T*)x, x_ld, C, HW, W, sc.nblk,
+                                                                                      sc.psum, sc.pmax, size_t(HW));
+      CDAN_CUDA_OK(cudaGetLastError());
+    }
+    gate_mlp_kernel<<<N, 256, (2 * C + 2 * (C / 16)) * sizeof(float), s>>>(sc.psum, sc.pmax, sc.nblk, C, HW, wt.w1, wt.b1,
+                                                                           wt.w2, wt.b2, sc.gate);
     CDAN_CUDA_OK(cudaGetLastError());
   }
-  gate_mlp_kernel<<<N, 256, (2 * C + 2 * (C / 16)) * sizeof(float), s>>>(sc.psum, sc.pmax, sc.nblk, C, HW, wt.w1, wt.b1,
-                                                                         wt.w2, wt.b2, sc.gate);
-  CDAN_CUDA_OK(cudaGetLastError());
   const size_t npix = size_t(N) * HW;
   const int lpp = vecs < 32 ? vecs : 32;
   if (C <= 512) {  // lanes cover the channels of a pixel in at most two 16-byte vectors each
@@ -316,7 +346,7 @@ int cbam_typed(const void* x, int x_ld, const void* mul, int mul_ld, void* out, 
 int cbam_pool_blocks(int H) { return (H + 1) / 2; }  // one partial per pair of image rows
 
 size_t cbam_scratch_floats(int N, int C, int H, int W) {
-  return 2 * size_t(N) * cbam_pool_blocks(H) * C + size_t(N) * C + 3 * size_t(N) * H * W + 64;
+  return 2 * size_t(N) * cbam_pool_blocks(H) * C + 3 * size_t(N) * C + 3 * size_t(N) * H * W + 64;
 }
 
 void cbam_scratch_carve(float* base, int N, int C, int H, int W, CbamScratch* sc) {
@@ -325,19 +355,20 @@ void cbam_scratch_carve(float* base, int N, int C, int H, int W, CbamScratch* sc
   sc->psum = base;
   sc->pmax = base + part;
   sc->gate = sc->pmax + part;
-  size_t off = 2 * part + size_t(N) * C;
+  sc->pooled = sc->gate + size_t(N) * C;
+  size_t off = 2 * part + 3 * size_t(N) * C;
   off = (off + 3) / 4 * 4;  // 16-byte alignment for the float2 reads of comp
   sc->comp = base + off;
   sc->sgate = sc->comp + 2 * size_t(N) * H * W;
 }
 
 int cbam_launch(DType dt, const void* x, int x_ld, const void* mul, int mul_ld, void* out, int out_ld, int N, int H,
-                int W, int C, const CbamWeights& wt, const CbamScratch& sc, bool pooled, cudaStream_t s) {
+                int W, int C, const CbamWeights& wt, const CbamScratch& sc, bool pooled, cudaStream_t s, const CbamBand* band) {
   if (C % 64 != 0 || C > 2048) return fail("cbam: gate_channels must be a multiple of 64 (<= 2048) for the CUDA path");
   if ((C & (C - 1)) != 0) return fail("cbam: gate_channels must be a power of two for the CUDA path");
   if (N > 65535) return fail("cbam: batch or image too large for one launch");
-  return dt == kF32 ? cbam_typed<float>(x, x_ld, mul, mul_ld, out, out_ld, N, H, W, C, wt, sc, pooled, s)
-                    : cbam_typed<bf16>(x, x_ld, mul, mul_ld, out, out_ld, N, H, W, C, wt, sc, pooled, s);
+  return dt == kF32 ? cbam_typed<float>(x, x_ld, mul, mul_ld, out, out_ld, N, H, W, C, wt, sc, pooled, s, band)
+                    : cbam_typed<bf16>(x, x_ld, mul, mul_ld, out, out_ld, N, H, W, C, wt, sc, pooled, s, band);
 }
 
 }  // namespace cdan

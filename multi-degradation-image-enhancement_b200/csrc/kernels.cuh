@@ -33,7 +33,15 @@ struct CbamScratch {
   float* gate = nullptr;   // [N][C]
   float* comp = nullptr;   // [N][H][W][2]
   float* sgate = nullptr;  // [N][H][W]
+  float* pooled = nullptr; // [2][N][C]  band mode: channel sums and maxima of the owned rows, all-reduced in place
   int nblk = 0;
+};
+// Row-tiled forward (band.cuh): the ChannelGate pools over the rows this band OWNS and all-reduces the statistics.
+struct BandComm;
+struct CbamBand {
+  int row0 = 0, rows = 0;   // owned rows of the (extended) tensor
+  int HW_full = 0;          // pixels of the whole image at this resolution (divisor of the mean)
+  BandComm* comm = nullptr;
 };
 int cbam_pool_blocks(int H);  // partial-reduction blocks per image: one per pair of image rows
 size_t cbam_scratch_floats(int N, int C, int H, int W);
@@ -41,7 +49,8 @@ void cbam_scratch_carve(float* base, int N, int C, int H, int W, CbamScratch* sc
 // out = SpatialGate(ChannelGate(x)) [* mul]  (mul = dense-block output of the decoder, models/cdan.py:133,141,149).
 // pooled = true: sc.psum / sc.pmax were already written by the kernel that produced x (up_add_launch with pool outputs).
 int cbam_launch(DType dt, const void* x, int x_ld, const void* mul, int mul_ld, void* out, int out_ld, int N, int H,
-                int W, int C, const CbamWeights& wt, const CbamScratch& sc, bool pooled, cudaStream_t s);
+                int W, int C, const CbamWeights& wt, const CbamScratch& sc, bool pooled, cudaStream_t s,
+                const CbamBand* band = nullptr);
 
 // ---- post-processing on planar fp32 NCHW images (utils/post_processing.py)
 enum PostOp : int { kContrast = 0, kColor = 1, kSharpen = 2, kDenoise = 3 };

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 
 #include "../../include/cdan_b200.h"
 #include "conv_umma.cuh"
@@ -25,8 +26,10 @@ struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) {
     cudaGetDevice(&prev);
-    if (prev != dev) cudaSetDevice(dev);
-    else prev = -1;
+    // always: since CUDA 12 cudaSetDevice also binds the primary context to the calling thread, which the driver-API calls
+    // of the kernels' launchers (cuTensorMapEncodeTiled) need in a host thread that has made no runtime call yet
+    cudaSetDevice(dev);
+    if (prev == dev) prev = -1;
   }
   ~DeviceGuard() {
     if (prev >= 0) cudaSetDevice(prev);
@@ -358,44 +361,60 @@ int conv_dispatch(cdan_plan* p, const ConvLayer& L, const ConvDesc& d, cudaStrea
 
 inline char* at(void* base, size_t elems, DType dt) { return (char*)base + elems * (dt == kF32 ? 4 : 2); }
 
+// `pre(l)` runs before layer l (0-3: growth layers, 4: transition) is launched: the row-tiled forward refreshes halo rows there.
+using LayerHook = std::function<int(int)>;
+
 int run_dense(cdan_plan* p, ConvId first, int N, int h, int w, void* D, int ld, int Cpad, void* DN, int Cout,
-              cudaStream_t s, float* out_nchw = nullptr) {
-  for (int l = 0; l < 4; ++l)
+              cudaStream_t s, float* out_nchw = nullptr, const LayerHook& pre = nullptr) {
+  for (int l = 0; l < 4; ++l) {
+    if (pre) CDAN_TRY(pre(l));
     CDAN_TRY(run_conv(p, ConvId(first + l), N, h, w, D, ld, at(D, Cpad + 16 * l, p->dt), ld, 0, s));
+  }
   (void)Cout;
+  if (pre) CDAN_TRY(pre(4));
   return run_conv(p, ConvId(first + 4), N, h, w, D, ld, DN, DN ? p->conv[first + 4].Cout : 0, 0, s, nullptr, out_nchw,
                   out_nchw ? 1 : 0);
 }
 
 // final dense block in the GROUP-PLANAR layout (bf16 tensor-core plans): plane g of D holds channels [16g, 16g+16) as a
 // dense [N][h][w][16] tensor; layer l reads planes 0..l and writes plane l+1, the transition reads all five.
-int run_dense_planar(cdan_plan* p, ConvId first, int N, int h, int w, void* D, cudaStream_t s, float* out_nchw) {
+int run_dense_planar(cdan_plan* p, ConvId first, int N, int h, int w, void* D, cudaStream_t s, float* out_nchw,
+                     const LayerHook& pre = nullptr) {
   const size_t gs = size_t(N) * h * w * 16;
-  for (int l = 0; l < 4; ++l)
+  for (int l = 0; l < 4; ++l) {
+    if (pre) CDAN_TRY(pre(l));
     CDAN_TRY(run_conv(p, ConvId(first + l), N, h, w, D, 16, at(D, gs * (1 + l), p->dt), 16, 0, s, nullptr, nullptr, 0, gs));
+  }
+  if (pre) CDAN_TRY(pre(4));
   return run_conv(p, ConvId(first + 4), N, h, w, D, 16, nullptr, 0, 0, s, nullptr, out_nchw, 1, gs);
 }
 
 // dense blocks 1-3 on a HYBRID concat buffer (bf16 tensor-core plans): the pooled ConvBlock output stays a compact NHWC
 // head of Cpre channels (the next ConvBlock, the decoder skip connection and the stage taps read it), the four 16-channel
 // groups the layers append are dense planes behind it.  Layer 0 reads only the head.
-int run_dense_hybrid(cdan_plan* p, ConvId first, int N, int h, int w, void* D, int Cpre, void* DN, cudaStream_t s) {
+int run_dense_hybrid(cdan_plan* p, ConvId first, int N, int h, int w, void* D, int Cpre, void* DN, cudaStream_t s,
+                     const LayerHook& pre = nullptr) {
   const size_t gs = size_t(N) * h * w * 16;
   void* planes = at(D, size_t(N) * h * w * Cpre, p->dt);
+  if (pre) CDAN_TRY(pre(0));
   CDAN_TRY(run_conv(p, first, N, h, w, D, Cpre, planes, 16, 0, s));
-  for (int l = 1; l < 4; ++l)
+  for (int l = 1; l < 4; ++l) {
+    if (pre) CDAN_TRY(pre(l));
     CDAN_TRY(run_conv(p, ConvId(first + l), N, h, w, D, Cpre, at(planes, gs * l, p->dt), 16, 0, s, nullptr, nullptr, 0, gs, planes, Cpre));
+  }
+  if (pre) CDAN_TRY(pre(4));
   return run_conv(p, ConvId(first + 4), N, h, w, D, Cpre, DN, p->conv[first + 4].Cout, 0, s, nullptr, nullptr, 0, gs, planes, Cpre);
 }
 
 int run_cbam(cdan_plan* p, int slot, const void* x, const void* mul, void* out, int N, int h, int w, bool pooled,
-             cudaStream_t s) {
+             cudaStream_t s, const CbamBand* band = nullptr) {
   const CbamLayer& L = p->cbam[slot];
   CbamScratch sc;
   cbam_scratch_carve(p->buf.cbam_scratch, N, L.C, h, w, &sc);
   SpanGuard span(p, s, "cbam|C" + std::to_string(L.C));
-  CDAN_TRY(cbam_launch(p->dt, x, L.C, mul, L.C, out, L.C, N, h, w, L.C, L.w, sc, pooled, s));
-  p->launches += pooled ? 4 : 5;
+  CDAN_TRY(cbam_launch(p->dt, x, L.C, mul, L.C, out, L.C, N, h, w, L.C, L.w, sc, pooled, s, band));
+  p->launches += band ? 6 : (pooled ? 4 : 5);
+  if (band) p->band_stats.allreduces += 2;
   return 0;
 }
 
@@ -436,7 +455,47 @@ void fill_stages(cdan_plan* p, int ld1, int ld2, int ld3, int fdl) {
   if (fdl) st["dec.final_in"] = {b.FD, 3, fdl, H, W};  // not materialised by the fused final dense block
 }
 
-int forward_impl(cdan_plan* p, cudaStream_t s, const float* x, float* y, int N, int H, int W) {
+// ------------------------------------------------------------------------------------------ row-tiled forward (band.cuh)
+// A tensor of the schedule as the band bookkeeping sees it: where its rows live and how many rows next to an artificial
+// (band) border are wrong.  Aliased tensors (the groups of an NHWC concat buffer) share one Ten.
+struct Ten {
+  void* p = nullptr;
+  int ld = 0;    // elements between pixels
+  int lvl = 0;   // resolution level: rows = H >> lvl
+  int dirt = 0;  // wrong rows at each artificial border (at this tensor's resolution)
+};
+struct BandRun {
+  cdan_plan* p;
+  cudaStream_t s;
+  int N, Hext, W, halo, dtop, dbot, Hfull;  // extended band; dtop/dbot = halo rows above / below (0 at the image border)
+  int D(int lvl) const { return halo >> lvl; }
+  // replace the halo rows of t by the neighbours' owned rows
+  int refresh(Ten& t) {
+    const size_t es = p->dt == kF32 ? 4 : 2;
+    const int d = D(t.lvl), h = Hext >> t.lvl;
+    const size_t row = size_t(W >> t.lvl) * t.ld * es;
+    HaloMsg m;
+    m.base = (char*)t.p;
+    m.img_stride = size_t(h) * row;
+    m.nimg = N;
+    m.bytes = size_t(d) * row;
+    m.top_recv = 0;
+    m.top_send = size_t(dtop >> t.lvl) * row;
+    m.bot_recv = size_t(h - (dbot >> t.lvl)) * row;
+    m.bot_send = m.bot_recv - m.bytes;
+    CDAN_TRY(p->band_comm->exchange(m, s));
+    const int nbrs = (p->band_comm->rank > 0) + (p->band_comm->rank + 1 < p->band_comm->nranks);
+    p->band_stats.exchanges += 1;
+    p->band_stats.halo_bytes_received += (long long)(m.bytes) * N * nbrs;
+    t.dirt = 0;
+    return 0;
+  }
+};
+
+// The CDAN forward.  br == nullptr: a whole image.  Otherwise x / y are the rows of the EXTENDED band and the schedule
+// interleaves halo refreshes: `need(t, e)` before a layer that looks e rows across the border (3x3: 1, 7x7: 3, bilinear x2:
+// checked as 2*dirt+1) refreshes t only if the dirty zone would otherwise grow past the halo into the owned rows.
+int forward_impl(cdan_plan* p, cudaStream_t s, const float* x, float* y, int N, int H, int W, BandRun* br = nullptr) {
   if (!p->loaded) return fail("cdan_forward: no weights loaded (call cdan_plan_load_weights first)");
   if (N <= 0 || H <= 0 || W <= 0) return fail("cdan_forward: empty input");
   if (H % 8 || W % 8)
@@ -449,54 +508,139 @@ int forward_impl(cdan_plan* p, cudaStream_t s, const float* x, float* y, int N, 
   p->launches = 0;
   p->N = N; p->H = H; p->W = W;
 
+  auto need = [&](Ten& t, int e) -> int { return br && t.dirt + e > br->D(t.lvl) ? br->refresh(t) : 0; };
+  auto need_up = [&](Ten& t) -> int { return br && 2 * t.dirt + 1 > br->D(t.lvl - 1) ? br->refresh(t) : 0; };
+  CbamBand cb[4];
+  auto band_of = [&](int slot, int lvl) -> const CbamBand* {
+    if (!br) return nullptr;
+    cb[slot].row0 = br->dtop >> lvl;
+    cb[slot].rows = (br->Hext - br->dtop - br->dbot) >> lvl;
+    cb[slot].HW_full = (br->Hfull >> lvl) * (W >> lvl);
+    cb[slot].comm = p->band_comm;
+    return &cb[slot];
+  };
+
   // ---- Encoder (models/cdan.py:70-98).  Pooled ConvBlock outputs land in channels [0,C) of the dense-block
   //      concat buffers, so they double as skip connections and as the first `features` entry.
   // Concat buffers of dense blocks 1-3: hybrid (compact NHWC head + group planes) on the tensor-core path, else NHWC.
   const bool hyb = dt == kBF16 && p->conv_impl == 0 && dense_hybrid_enabled();
   const int ld1 = hyb ? 64 : 128, ld2 = hyb ? 128 : 192, ld3 = hyb ? 256 : 320;
-  CDAN_TRY(run_conv(p, ENC1, N, H, W, nullptr, 0, b.D1, ld1, 1, s, x));
-  if (hyb) CDAN_TRY(run_dense_hybrid(p, D1L0, N, H2, W2, b.D1, 64, b.DN1, s));
-  else CDAN_TRY(run_dense(p, D1L0, N, H2, W2, b.D1, 128, 64, b.DN1, 64, s));
+  // dense block on concat buffer D at level lvl: head = the block input, g[1..4] = the groups the layers append (hybrid:
+  // planes behind the compact head; NHWC: the same rows as the head, one Ten)
+  struct DenseTens {
+    Ten head, plane[4], out;
+    Ten* g[5];
+  };
+  auto dense_tens = [&](DenseTens& d, void* D, int Cpre, int ld, int lvl, int h, int w, bool planar, void* DN, int Cdn, int head_dirt) {
+    d.head = Ten{D, ld, lvl, head_dirt};
+    d.g[0] = &d.head;
+    for (int l = 0; l < 4; ++l) {
+      d.plane[l] = Ten{at(at(D, size_t(N) * h * w * Cpre, dt), size_t(N) * h * w * 16 * l, dt), 16, lvl, 0};
+      d.g[1 + l] = planar ? &d.plane[l] : &d.head;
+    }
+    d.out = Ten{DN, Cdn, lvl, 0};
+  };
+  auto dense_hook = [&](DenseTens& d) -> LayerHook {
+    if (!br) return nullptr;
+    return [&d, &need](int l) -> int {  // layer l reads groups 0..l (3x3: one row across the border; transition l = 4: none)
+      const int e = l < 4 ? 1 : 0, last = l < 4 ? l : 4;
+      int worst = 0;
+      for (int i = 0; i <= last; ++i) {
+        CDAN_TRY(need(*d.g[i], e));
+        worst = std::max(worst, d.g[i]->dirt);
+      }
+      Ten& o = l < 4 ? *d.g[l + 1] : d.out;
+      o.dirt = std::max(o.p == d.head.p && l < 4 ? o.dirt : 0, worst + e);
+      return 0;
+    };
+  };
+  DenseTens t1, t2, t3;
+  CDAN_TRY(run_conv(p, ENC1, N, H, W, nullptr, 0, b.D1, ld1, 1, s, x));  // input rows are never dirty: conv (+1), pool (ceil /2)
+  dense_tens(t1, b.D1, 64, ld1, 1, H2, W2, hyb, b.DN1, 64, 1);
+  if (hyb) CDAN_TRY(run_dense_hybrid(p, D1L0, N, H2, W2, b.D1, 64, b.DN1, s, dense_hook(t1)));
+  else CDAN_TRY(run_dense(p, D1L0, N, H2, W2, b.D1, 128, 64, b.DN1, 64, s, nullptr, dense_hook(t1)));
+  CDAN_TRY(need(t1.head, 1));
   CDAN_TRY(run_conv(p, ENC2, N, H2, W2, b.D1, ld1, b.D2, ld2, 1, s));
-  if (hyb) CDAN_TRY(run_dense_hybrid(p, D2L0, N, H4, W4, b.D2, 128, b.DN2, s));
-  else CDAN_TRY(run_dense(p, D2L0, N, H4, W4, b.D2, 192, 128, b.DN2, 128, s));
+  dense_tens(t2, b.D2, 128, ld2, 2, H4, W4, hyb, b.DN2, 128, (t1.head.dirt + 2) / 2);
+  if (hyb) CDAN_TRY(run_dense_hybrid(p, D2L0, N, H4, W4, b.D2, 128, b.DN2, s, dense_hook(t2)));
+  else CDAN_TRY(run_dense(p, D2L0, N, H4, W4, b.D2, 192, 128, b.DN2, 128, s, nullptr, dense_hook(t2)));
+  CDAN_TRY(need(t2.head, 1));
   CDAN_TRY(run_conv(p, ENC3, N, H4, W4, b.D2, ld2, b.D3, ld3, 1, s));
-  if (hyb) CDAN_TRY(run_dense_hybrid(p, D3L0, N, H8, W8, b.D3, 256, b.DN3, s));
-  else CDAN_TRY(run_dense(p, D3L0, N, H8, W8, b.D3, 320, 256, b.DN3, 256, s));
+  dense_tens(t3, b.D3, 256, ld3, 3, H8, W8, hyb, b.DN3, 256, (t2.head.dirt + 2) / 2);
+  if (hyb) CDAN_TRY(run_dense_hybrid(p, D3L0, N, H8, W8, b.D3, 256, b.DN3, s, dense_hook(t3)));
+  else CDAN_TRY(run_dense(p, D3L0, N, H8, W8, b.D3, 320, 256, b.DN3, 256, s, nullptr, dense_hook(t3)));
+  CDAN_TRY(need(t3.head, 1));
   CDAN_TRY(run_conv(p, ENC4, N, H8, W8, b.D3, ld3, b.E4, 512, 0, s));
+  Ten E4{b.E4, 512, 3, t3.head.dirt + 1};
   // ---- bottleneck CBAM(512) (models/cdan.py:173)
-  CDAN_TRY(run_cbam(p, 0, b.E4, nullptr, b.B0, N, H8, W8, false, s));
+  CDAN_TRY(need(E4, 3));
+  CDAN_TRY(run_cbam(p, 0, b.E4, nullptr, b.B0, N, H8, W8, false, s, band_of(0, 3)));
+  Ten B0{b.B0, 512, 3, E4.dirt + 3};
   // ---- Decoder (models/cdan.py:126-159)
+  CDAN_TRY(need(B0, 1));
   CDAN_TRY(run_conv(p, DEC1, N, H8, W8, b.B0, 512, b.T1, 256, 0, s));
   CDAN_TRY(run_up_add(p, 1, b.T1, 256, b.D3, ld3, b.A1, N, H8, W8, 0, s));
-  CDAN_TRY(run_cbam(p, 1, b.A1, b.DN3, b.C1, N, H8, W8, true, s));
+  Ten A1{b.A1, 256, 3, std::max(B0.dirt + 1, t3.head.dirt)};
+  CDAN_TRY(need(A1, 3));
+  CDAN_TRY(run_cbam(p, 1, b.A1, b.DN3, b.C1, N, H8, W8, true, s, band_of(1, 3)));
+  Ten C1{b.C1, 256, 3, std::max(A1.dirt + 3, t3.out.dirt)};
+  CDAN_TRY(need(C1, 1));
   CDAN_TRY(run_conv(p, DEC2, N, H8, W8, b.C1, 256, b.T2, 128, 0, s));
+  Ten T2{b.T2, 128, 3, C1.dirt + 1};
+  CDAN_TRY(need_up(T2));
   CDAN_TRY(run_up_add(p, 2, b.T2, 128, b.D2, ld2, b.U2, N, H4, W4, 1, s));
-  CDAN_TRY(run_cbam(p, 2, b.U2, b.DN2, b.C2, N, H4, W4, true, s));
+  Ten U2{b.U2, 128, 2, std::max(2 * T2.dirt + 1, t2.head.dirt)};
+  CDAN_TRY(need(U2, 3));
+  CDAN_TRY(run_cbam(p, 2, b.U2, b.DN2, b.C2, N, H4, W4, true, s, band_of(2, 2)));
+  Ten C2{b.C2, 128, 2, std::max(U2.dirt + 3, t2.out.dirt)};
+  CDAN_TRY(need(C2, 1));
   CDAN_TRY(run_conv(p, DEC3, N, H4, W4, b.C2, 128, b.T3, 64, 0, s));
+  Ten T3{b.T3, 64, 2, C2.dirt + 1};
+  CDAN_TRY(need_up(T3));
   CDAN_TRY(run_up_add(p, 3, b.T3, 64, b.D1, ld1, b.U3, N, H2, W2, 1, s));
-  CDAN_TRY(run_cbam(p, 3, b.U3, b.DN1, b.C3, N, H2, W2, true, s));
+  Ten U3{b.U3, 64, 1, std::max(2 * T3.dirt + 1, t1.head.dirt)};
+  CDAN_TRY(need(U3, 3));
+  CDAN_TRY(run_cbam(p, 3, b.U3, b.DN1, b.C3, N, H2, W2, true, s, band_of(3, 1)));
+  Ten C3{b.C3, 64, 1, std::max(U3.dirt + 3, t1.out.dirt)};
+  CDAN_TRY(need(C3, 1));
   CDAN_TRY(run_conv(p, DEC4, N, H2, W2, b.C3, 64, b.T4, 8, 0, s));
+  Ten T4{b.T4, 8, 1, C3.dirt + 1};
+  int out_dirt = 0;
   if (use_fd_fused(p)) {
     // bilinear x2 + x, the final DenseBlock(3,3,16,4) and the sigmoid as ONE kernel (dense_fused.cu): the 67-channel
-    // full-resolution concat never exists in HBM
+    // full-resolution concat never exists in HBM.  Band mode: bilinear (2d+1) and four 3x3 layers (+4) inside the kernel.
+    if (br && 2 * T4.dirt + 5 > br->D(0)) CDAN_TRY(br->refresh(T4));
+    out_dirt = 2 * T4.dirt + 5;
     SpanGuard span(p, s, "conv|decoder.final_dense|fused");
     CDAN_TRY(fused_fd_launch(*p->fd_fused, b.T4, 8, x, y, N, H, W, s));
     p->launches += 1;
     fill_stages(p, ld1, ld2, ld3, 0);
-    return 0;
+  } else {
+    // The final dense block's concat buffer is group-planar on the tensor-core path, NHWC otherwise.
+    const bool fd_planar = dt == kBF16 && p->conv_impl == 0 && fd_planar_enabled();
+    const int fdl = fd_planar ? 16 : fd_ld();
+    CDAN_TRY(need_up(T4));
+    { SpanGuard span(p, s, "glue|up_add_input"); CDAN_TRY(up_add_input_launch(dt, b.T4, 8, x, b.FD, fdl, 16, N, H, W, s)); }
+    p->launches += 1;
+    DenseTens tf;
+    dense_tens(tf, b.FD, 16, fdl, 0, H, W, fd_planar, nullptr, 0, 2 * T4.dirt + 1);
+    // final DenseBlock(3,3,16,4) + sigmoid, written straight to the caller's fp32 NCHW output
+    if (fd_planar) CDAN_TRY(run_dense_planar(p, FDL0, N, H, W, b.FD, s, y, dense_hook(tf)));
+    else CDAN_TRY(run_dense(p, FDL0, N, H, W, b.FD, fd_ld(), 16, nullptr, 3, s, y, dense_hook(tf)));
+    out_dirt = tf.out.dirt;
+    fill_stages(p, ld1, ld2, ld3, fdl);
   }
-  // The final dense block's concat buffer is group-planar on the tensor-core path, NHWC otherwise.
-  const bool fd_planar = dt == kBF16 && p->conv_impl == 0 && fd_planar_enabled();
-  const int fdl = fd_planar ? 16 : fd_ld();
-  { SpanGuard span(p, s, "glue|up_add_input"); CDAN_TRY(up_add_input_launch(dt, b.T4, 8, x, b.FD, fdl, 16, N, H, W, s)); }
-  p->launches += 1;
-  // final DenseBlock(3,3,16,4) + sigmoid, written straight to the caller's fp32 NCHW output
-  if (fd_planar) CDAN_TRY(run_dense_planar(p, FDL0, N, H, W, b.FD, s, y));
-  else CDAN_TRY(run_dense(p, FDL0, N, H, W, b.FD, fd_ld(), 16, nullptr, 3, s, y));
-
-  fill_stages(p, ld1, ld2, ld3, fdl);
+  if (br && out_dirt > br->D(0)) return fail("row-tiled forward: internal error, the output's dirty zone reaches the owned rows");
   return 0;
+}
+
+int forward_band_impl(cdan_plan* p, cudaStream_t s, const float* x_ext, float* y_ext, int N, int H, int W, int halo) {
+  if (!p->band_comm) return fail("cdan_forward_band: no band transport attached (cdan_plan_band_attach_local / _nccl)");
+  int rows[4];
+  CDAN_TRY(band_rows(H, p->band_comm->nranks, p->band_comm->rank, halo, rows));
+  BandRun br{p, s, N, rows[3] - rows[2], W, halo, rows[0] - rows[2], rows[3] - rows[1], H};
+  p->band_stats = BandStats{};
+  return forward_impl(p, s, x_ext, y_ext, N, br.Hext, W, &br);
 }
 
 }  // namespace
@@ -534,6 +678,7 @@ int cdan_plan_destroy(cdan_plan* p) {
   if (!p) return 0;
   DeviceGuard g(p->device);
   free_weights(p);
+  delete p->band_comm;
   if (p->ws) cudaFree(p->ws);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
   if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
@@ -711,6 +856,12 @@ static int forward_host_impl(cdan_plan* p, const void* x_host, void* y_host, int
   }
   CDAN_CUDA_OK(cudaStreamSynchronize(p->d2h_stream));
   return 0;
+}
+
+int cdan_forward_band(cdan_plan* p, void* stream, const float* x_ext, float* y_ext, int N, int H, int W, int halo) {
+  if (!p || !x_ext || !y_ext) return fail("cdan_forward_band: NULL argument");
+  DeviceGuard g(p->device);
+  return forward_band_impl(p, (cudaStream_t)stream, x_ext, y_ext, N, H, W, halo);
 }
 
 int cdan_forward_host(cdan_plan* p, const float* x_host, float* y_host, int N, int H, int W) {

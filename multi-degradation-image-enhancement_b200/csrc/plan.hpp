@@ -4,6 +4,7 @@
 #include <string>
 #include <vector>
 
+#include "band.cuh"
 #include "common.cuh"
 #include "conv.cuh"
 #include "dense_fused.cuh"
@@ -67,6 +68,9 @@ struct cdan_plan {
   cdan::CbamLayer cbam[4];
   bool fd_fused_on = true;                // option "fd_fused"
   cdan::FusedFdPack* fd_fused = nullptr;  // final dense block as one kernel (bf16 tensor-core plans)
+  // spatial row tiling (band.cuh): transport to the neighbouring bands, counters of the most recent banded forward
+  cdan::BandComm* band_comm = nullptr;
+  cdan::BandStats band_stats;
   std::vector<void*> owned;
   void* ws = nullptr;
   size_t ws_bytes = 0;
