@@ -47,11 +47,12 @@ FLOP_PER_PIXEL = 252770  # algorithmic conv FLOPs (2*MAC, unpadded), SURVEY 8(d)
 DENSE3X3 = {f"{blk}.layers.{l}": (c0 + 16 * l, div)
             for blk, c0, div in (("encoder.dense1", 64, 2), ("encoder.dense2", 128, 4), ("encoder.dense3", 256, 8),
                                  ("decoder.final_dense", 3, 1)) for l in range(4)}
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per 32 x 1080p step from the `ncu --set full` capture
-# summarised in profiles/r01_allconv_ncu.md: the 16 dense-block 3x3 launches, and all 29 convolution launches.
-DENSE3X3_NCU_TRAFFIC_BYTES = 52039405000
-ALLCONV_NCU_TRAFFIC_BYTES = 89809026000
-CBAM_NCU_TRAFFIC_BYTES = None  # filled from profiles/r02_* once captured
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per 32 x 1080p step from the `ncu --set full` capture of ALL
+# launches of a step summarised in profiles/r02_step_ncu.md: the 12 dense-block 3x3 launches of dense blocks 1-3 (the final
+# dense block is one fused kernel), all 24 convolution launches, and the CBAM kernels.
+DENSE3X3_NCU_TRAFFIC_BYTES = 22317480000
+ALLCONV_NCU_TRAFFIC_BYTES = 50522824000
+CBAM_NCU_TRAFFIC_BYTES = 19543534000
 
 
 def measured_peaks():
@@ -195,8 +196,119 @@ def run_reference(args, rank, world, emit):
 
 
 def workload_name(args, n):
+    if args.config == "c5":
+        return f"CDAN forward {n}x3x{args.height}x{args.width}, ONE image batch split into row bands over the GPUs (BASELINE C5)"
     tag = {"c3": "BASELINE C3", "c2": "BASELINE C2"}[args.config]
     return f"CDAN forward {n}x3x{args.height}x{args.width} per GPU ({tag}), batch-sharded, no collective"
+
+
+def run_c5(args, rank, world, dev, dist, cpu_baseline, numa, emit):
+    """BASELINE config 5: ONE large image (default 1 x 3 x 2160 x 3840) split into row bands over the GPUs
+    (spatial_tiling.NcclBandedCDAN: recompute halos, halo refreshes by ncclSend/ncclRecv, ChannelGate all-reduce).
+    At N = 1 the same image runs through the untiled forward.  Strong scaling: value = image megapixels / step time."""
+    import cdan_b200_native as native
+    import spatial_tiling as st
+    n, h, w = args.batch, args.height, args.width
+    sd = default_weights(42)
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    x_host = synthetic_batch(n, h, w, seed=42).pin_memory()  # the same image on every rank
+    if world > 1:
+        runner = st.NcclBandedCDAN(sd, args.dtype, dev, halo=args.halo)
+        plan = runner.plan
+        r0, r1, e0, e1 = runner.rows(h)
+    else:
+        plan = native.Plan(dev, args.dtype)
+        plan.load_state_dict(sd)
+        r0, r1, e0, e1 = 0, h, 0, h
+    x_ext_host = x_host[:, :, e0:e1].contiguous().pin_memory()
+    y_own_host = torch.empty((n, 3, r1 - r0, w), dtype=torch.float32).pin_memory()
+    x_ext = x_ext_host.to(dev)
+    y_ext = torch.empty_like(x_ext)
+
+    def fwd():
+        if world > 1:
+            plan.forward_band(x_ext, h, args.halo, out=y_ext)
+        else:
+            plan.forward(x_ext, out=y_ext)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)
+    t_warm0 = time.perf_counter()
+    for _ in range(args.warmup):
+        fwd()
+    barrier()
+    # device-timed: per-forward CUDA events (an L2 flush between forwards, untimed), summed; max over ranks
+    t_region0 = time.perf_counter()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e_a, e_b in evs:
+        flush.fill_(1)
+        if dist is not None:
+            dist.barrier()  # bands start a forward together (a collective schedule)
+        e_a.record()
+        fwd()
+        e_b.record()
+    barrier()
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop(t_region0, time.perf_counter(), t_warm0)
+    launches = plan.last_launch_count
+    stats = plan.band_stats() if world > 1 else {"halo_exchanges": 0, "halo_bytes_received": 0, "allreduces": 0}
+
+    # end to end: pinned host rows of the band (halo included) -> H2D -> banded forward -> D2H of the OWNED rows
+    def e2e_once():
+        x_ext.copy_(x_ext_host, non_blocking=True)
+        fwd()
+        y_own_host.copy_(y_ext[:, :, r0 - e0:r1 - e0], non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    e2e_once()
+    barrier()
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        if dist is not None:
+            dist.barrier()
+        e2e_once()
+    e2e_s = (time.perf_counter() - t0) / steps
+    t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, e2e_s = float(t[0]) / args.steps, float(t[1])
+    mp = n * h * w / 1e6
+    if rank == 0:
+        peaks = measured_peaks()
+        flops = FLOP_PER_PIXEL * n * h * w
+        line = {
+            "metric": "megapixels/sec CDAN fwd (one 4K image in row bands, bf16)" if args.dtype == "bf16" else "megapixels/sec CDAN fwd (row bands)",
+            "value": mp / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic", "images_per_s": n / (ms_step * 1e-3),
+            "config": {"workload": workload_name(args, n), "name": "c5", "batch": n, "height": h, "width": w,
+                       "bands": world, "halo_rows": args.halo if world > 1 else 0,
+                       "rows_rank0": {"owned": [r0, r1], "extended": [e0, e1]},
+                       "halo_refreshes_per_forward": stats["halo_exchanges"], "allreduces_per_forward": stats["allreduces"],
+                       "halo_bytes_received_rank0": stats["halo_bytes_received"],
+                       "weights": "torch.manual_seed(42); CDAN() default init (random)",
+                       "l2": "256 MB buffer written between timed forwards (L2 flush); per-forward CUDA events summed",
+                       "parallelism": f"rows{world}" if world > 1 else "untiled", "host_numa": numa},
+            "clocks": clocks,
+            "e2e": {"value": mp / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(x_ext_host.numel() * 4),
+                    "d2h_bytes_per_step": int(y_own_host.numel() * 4), "ms_per_step": e2e_s * 1e3,
+                    "api": "pinned host rows of the band -> H2D -> cdan_forward_band (NCCL halo refreshes) -> D2H of the owned rows"},
+            "gpu_launches": launches * args.steps,
+            "roofline": {"bound": "tensor", "kernel": "whole banded forward (latency-bound: launches + halo refreshes; see DESIGN.md 6)",
+                         "achieved": flops / (ms_step * 1e-3) / 1e12, "peak": peaks["tensor"] * world, "unit": "TFLOP/s",
+                         "frac": flops / (ms_step * 1e-3) / 1e12 / (peaks["tensor"] * world), "traffic": None,
+                         "peak_source": peaks["source"] + " (sustained) x n_gpus"},
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        emit(line)
 
 
 def main():
@@ -205,7 +317,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c3", choices=["c3", "c2"])
+    ap.add_argument("--config", default="c3", choices=["c3", "c2", "c5"])
+    ap.add_argument("--halo", type=int, default=24, help="c5: recompute halo rows per interior band side")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the config's batch)")
     ap.add_argument("--height", type=int, default=None)
@@ -216,12 +329,14 @@ def main():
     ap.add_argument("--layers", action="store_true", help="print the per-launch timing table to stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    cfg_batch, cfg_h, cfg_w = {"c3": (32, 1080, 1920), "c2": (64, 256, 256)}[args.config]
+    cfg_batch, cfg_h, cfg_w = {"c3": (32, 1080, 1920), "c2": (64, 256, 256), "c5": (1, 2160, 3840)}[args.config]
     args.height = args.height or cfg_h
     args.width = args.width or cfg_w
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.config == "c5":
+        args.scaling = "strong"  # one image, split by rows: total work is fixed
     if args.batch is None:
-        args.batch = max(1, cfg_batch // world_env) if args.scaling == "strong" else cfg_batch
+        args.batch = cfg_batch if args.config == "c5" else (max(1, cfg_batch // world_env) if args.scaling == "strong" else cfg_batch)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -263,6 +378,13 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+
+    if args.config == "c5":
+        run_c5(args, rank, world, dev, dist, cpu_baseline, numa, emit)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     from models.cdan import CDAN
 
@@ -390,14 +512,16 @@ def main():
                               "kernel_ms_per_step": cbam_ms, "note": "achieved = compulsory 144 B/px over the 4 CBAM sites"},
             "glue_ms_per_step": glue_ms,
         }
-        dense_ms = sum(v[0] for k, v in spans.items() if k.split("|")[1] in DENSE3X3) / args.steps
-        dense_bytes = sum(2.0 * (cin + 16) * n * (h // div) * (w // div) for cin, div in DENSE3X3.values())
+        # only the layers that ran as launches of their own (the fused final dense block has no per-layer spans)
+        dense_run = {k.split("|")[1] for k in spans if k.split("|")[1] in DENSE3X3}
+        dense_ms = sum(v[0] for k, v in spans.items() if k.split("|")[1] in dense_run) / args.steps
+        dense_bytes = sum(2.0 * (cin + 16) * n * (h // div) * (w // div) for name, (cin, div) in DENSE3X3.items() if name in dense_run)
         if dense_ms > 0:
             gbs = dense_bytes / (dense_ms * 1e-3) / 1e9
             line["roofline_dense"] = {
                 "bound": "hbm", "kernel": "conv_stream2_kernel<4,0,GP> (dense-block 3x3 launches of a step that are not fused)",
                 "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-                "traffic": DENSE3X3_NCU_TRAFFIC_BYTES if c3_full else None,
+                "traffic": DENSE3X3_NCU_TRAFFIC_BYTES if c3_full and len(dense_run) == 12 else None,
                 "algorithmic_bytes_per_step": dense_bytes, "kernel_ms_per_step": dense_ms,
                 "kernel_share_of_step": dense_ms / ms_step if ms_step else None}
         if cpu_baseline is not None:
