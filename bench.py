@@ -198,8 +198,105 @@ def run_reference(args, rank, world, emit):
 def workload_name(args, n):
     if args.config == "c5":
         return f"CDAN forward {n}x3x{args.height}x{args.width}, ONE image batch split into row bands over the GPUs (BASELINE C5)"
+    if args.config == "c4":
+        return (f"multi-degradation routing: MultiHeadClassifier (ResNet18, torch) -> thresholds -> 5 per-degradation CDAN weight sets "
+                f"on a mixed synthetic batch {n}x3x{args.height}x{args.width} per GPU (BASELINE C4)")
     tag = {"c3": "BASELINE C3", "c2": "BASELINE C2"}[args.config]
     return f"CDAN forward {n}x3x{args.height}x{args.width} per GPU ({tag}), batch-sharded, no collective"
+
+
+def run_c4(args, rank, world, dev, dist, numa, emit):
+    """BASELINE config 4: a mixed synthetic batch per GPU (reference degradation functions, 0-3 degradations per image) is
+    classified by the multi-label classifier (ResNet18 on torch), thresholded per class and routed through the CDAN weight
+    set of every flagged degradation (routing.MultiDegradationPipeline).  Weights are seeded random (no checkpoints
+    offline), so the classifier's thresholds are set to the per-class median probability of the batch: every enhancer
+    receives about half of the images, ~2.5 CDAN passes per image.  A step = classify + route + enhance one batch."""
+    import cdan_b200_native as native
+    from classification.multilabel_classifier import DEGRADATIONS, MultiHeadClassifier, predict_probs
+    from models.cdan import CDAN
+    from routing import ENHANCER_CLASSES, MultiDegradationPipeline, synthetic_mixed_batch
+    n, h, w = args.batch, args.height, args.width
+    torch.manual_seed(7)
+    clf = MultiHeadClassifier().to(dev).eval()
+    enhancers = {}
+    for k, name in enumerate(ENHANCER_CLASSES):
+        net = CDAN().set_compute_dtype(args.dtype)
+        net.load_state_dict(default_weights(100 + k))
+        enhancers[name] = net.to(dev).eval()
+    xu_host, _ = synthetic_mixed_batch(n, h, w, seed=1000 + rank)
+    xu_host = xu_host.pin_memory()
+    yu_host = torch.empty_like(xu_host).pin_memory()
+    x = (xu_host.to(dev).permute(0, 3, 1, 2).float() / 255).contiguous()
+    with torch.no_grad():
+        probs, _ = predict_probs(clf, x)
+    th = [float(probs[:, i].median()) for i in range(len(DEGRADATIONS))]
+    pipe = MultiDegradationPipeline(clf, enhancers, thresholds=th)
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)
+    t_warm0 = time.perf_counter()
+    for _ in range(args.warmup):
+        y = pipe(x)
+    barrier()
+    launches = sum(e.native_plan(dev).last_launch_count for e in enhancers.values())
+    t_region0 = time.perf_counter()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in evs:
+        flush.fill_(1)
+        a.record()
+        y = pipe(x)
+        b.record()
+    barrier()
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop(t_region0, time.perf_counter(), t_warm0)
+    passes = sum(pipe.router.last_bucket_sizes.values())
+
+    def e2e_once():  # uint8 host image batch -> H2D -> /255 -> classify + route + enhance -> x255 uint8 -> D2H
+        xd = xu_host.to(dev, non_blocking=True).permute(0, 3, 1, 2).float().mul_(1.0 / 255).contiguous()
+        yu_host.copy_(native.quantize_u8(pipe(xd)), non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    e2e_once()
+    barrier()
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_once()
+    e2e_s = (time.perf_counter() - t0) / steps
+    t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, e2e_s = float(t[0]) / args.steps, float(t[1])
+    if rank == 0:
+        mp = world * n * h * w / 1e6
+        peaks = measured_peaks()
+        flops = FLOP_PER_PIXEL * passes * h * w  # CDAN passes only (the classifier adds ~1.8 GFLOP per image on cuDNN)
+        emit({
+            "metric": "images/sec multi-degradation routing (classifier + per-degradation CDAN, bf16)", "value": world * n / (ms_step * 1e-3),
+            "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "megapixels_per_s": mp / (ms_step * 1e-3),
+            "config": {"workload": workload_name(args, n), "name": "c4", "batch_per_gpu": n, "height": h, "width": w,
+                       "classes": DEGRADATIONS, "routed_classes": ENHANCER_CLASSES, "bucket_sizes_rank0": pipe.router.last_bucket_sizes,
+                       "cdan_passes_per_image": passes / n, "weights": "seeded random (classifier and 5 CDAN sets); thresholds = per-class median",
+                       "l2": "256 MB buffer written between timed steps (L2 flush); per-step CUDA events summed",
+                       "parallelism": f"dp{world}", "host_numa": numa},
+            "clocks": clocks,
+            "e2e": {"value": world * n / e2e_s, "unit": "img/s", "h2d_bytes_per_step": n * h * w * 3, "d2h_bytes_per_step": n * h * w * 3,
+                    "ms_per_step": e2e_s * 1e3, "api": "uint8 host batch -> H2D -> MultiDegradationPipeline -> cdan_quantize_u8 -> D2H"},
+            "gpu_launches": launches * args.steps,
+            "roofline": {"bound": "tensor", "kernel": "CDAN convolution FLOPs of the routed passes over the whole step (classifier and routing included in the time)",
+                         "achieved": flops / (ms_step * 1e-3) / 1e12, "peak": peaks["tensor"], "unit": "TFLOP/s",
+                         "frac": flops / (ms_step * 1e-3) / 1e12 / peaks["tensor"], "traffic": None,
+                         "peak_source": peaks["source"] + " (sustained)"},
+        })
 
 
 def run_c5(args, rank, world, dev, dist, cpu_baseline, numa, emit):
@@ -317,7 +414,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c3", choices=["c3", "c2", "c5"])
+    ap.add_argument("--config", default="c3", choices=["c3", "c2", "c4", "c5"])
     ap.add_argument("--halo", type=int, default=24, help="c5: recompute halo rows per interior band side")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the config's batch)")
@@ -329,7 +426,7 @@ def main():
     ap.add_argument("--layers", action="store_true", help="print the per-launch timing table to stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    cfg_batch, cfg_h, cfg_w = {"c3": (32, 1080, 1920), "c2": (64, 256, 256), "c5": (1, 2160, 3840)}[args.config]
+    cfg_batch, cfg_h, cfg_w = {"c3": (32, 1080, 1920), "c2": (64, 256, 256), "c4": (64, 256, 384), "c5": (1, 2160, 3840)}[args.config]
     args.height = args.height or cfg_h
     args.width = args.width or cfg_w
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
@@ -379,6 +476,12 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.config == "c4":
+        run_c4(args, rank, world, dev, dist, numa, emit)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     if args.config == "c5":
         run_c5(args, rank, world, dev, dist, cpu_baseline, numa, emit)
         if dist is not None:
