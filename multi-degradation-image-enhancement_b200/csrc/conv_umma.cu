@@ -84,8 +84,8 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
   uint8_t* sA = smem;
   uint8_t* sB = sA + size_t(P.SA) * P.a_stage_bytes;
   uint8_t* sTail = sB + size_t(P.SB) * P.b_stage_bytes + 1024;  // 1 KB slack for garbage-row over-reads
-  float* s_bias = reinterpret_cast<float*>(sTail);                // [NT]
-  float* s_xbuf = s_bias + 256;                                   // pool exchange: [2][2 warps][32 lanes][32 cols]
+  float* s_bias = reinterpret_cast<float*>(sTail);                // [2 epilogue groups][NT]
+  float* s_xbuf = s_bias + 2 * 256;                               // pool exchange per epilogue group: [2][2 pairs][16 cols][32 lanes]
 
   __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], raw_full[kMaxSA], b_full[kMaxSB], b_empty[kMaxSB], acc_full[2],
       acc_empty[2];
@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int total_work = P.ntiles * P.npass;
   constexpr int kProducerWarps = 8;
+  constexpr int kEpiGroups = IN_MODE == kInTma ? 2 : 1;  // TMA mode has no builder warps: warps 8-11 drain accumulators too
 
   if (tid == 0) {
     for (int i = 0; i < P.SA; ++i) {
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&acc_full[i], 1);
-      ptx::mbar_init(&acc_empty[i], 4);
+      ptx::mbar_init(&acc_empty[i], 4 * kEpiGroups);
     }
     ptx::fence_mbar_init();
     if (IN_MODE != kInNchw3) ptx::prefetch_tmap(&tmapA);
@@ -122,22 +123,12 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    // ============================================================ producer: B ring (+ A via TMA)
+    // ============================================================ producer of the weight (B) ring
     if (lane == 0) {
-      int sa = 0, pa = 0, sb = 0, pb = 0;
+      int sb = 0, pb = 0;
       for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-        const int t = work / P.npass, pass = work - t * P.npass;
-        int n, h0, w0;
-        decode_tile(P, t, n, h0, w0);
+        const int pass = work % P.npass;
         for (int c = 0; c < P.nchunks; ++c) {
-          if (IN_MODE != kInNchw3) {
-            // TMA mode: the tile feeds the MMA directly; producer mode: it lands "raw" and warps 8-15 activate it
-            uint64_t* full = IN_MODE == kInTma ? &a_full[sa] : &raw_full[sa];
-            ptx::mbar_wait(&a_empty[sa], pa ^ 1);
-            ptx::mbar_arrive_expect_tx(full, uint32_t(P.a_rows) * 128u);
-            ptx::tma_load_4d(sA + size_t(sa) * P.a_stage_bytes, &tmapA, c * 64, w0 - P.halo, h0 - P.halo, n, full);
-            if (++sa == P.SA) { sa = 0; pa ^= 1; }
-          }
           const uint8_t* wsrc = P.wpack + (size_t(pass) * P.nchunks + c) * P.taps * (size_t(P.NT) * 128);
           for (int j = 0; j < P.bst_per_chunk; ++j) {
             const int ntap = min(P.tps, P.taps - j * P.tps);
@@ -147,6 +138,26 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
             ptx::bulk_g2s(sB + size_t(sb) * P.b_stage_bytes, wsrc + size_t(j) * P.tps * P.NT * 128, bytes, &b_full[sb]);
             if (++sb == P.SB) { sb = 0; pb ^= 1; }
           }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ============================================================ producer of the activation (A) tiles via TMA.  Its own
+    // thread: behind the weight ring in one program order, the tile of chunk c+1 was requested only ~4 weight stages
+    // (~2 us) before the MMAs needed it — less than a loaded DRAM round trip — and the tensor pipe idled on a_full.
+    if (IN_MODE != kInNchw3 && lane == 0) {
+      int sa = 0, pa = 0;
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int t = work / P.npass;
+        int n, h0, w0;
+        decode_tile(P, t, n, h0, w0);
+        for (int c = 0; c < P.nchunks; ++c) {
+          // TMA mode: the tile feeds the MMA directly; producer mode: it lands "raw" and warps 8-15 activate it
+          uint64_t* full = IN_MODE == kInTma ? &a_full[sa] : &raw_full[sa];
+          ptx::mbar_wait(&a_empty[sa], pa ^ 1);
+          ptx::mbar_arrive_expect_tx(full, uint32_t(P.a_rows) * 128u);
+          ptx::tma_load_4d(sA + size_t(sa) * P.a_stage_bytes, &tmapA, c * 64, w0 - P.halo, h0 - P.halo, n, full);
+          if (++sa == P.SA) { sa = 0; pa ^= 1; }
         }
       }
     }
@@ -203,21 +214,33 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
       }
       if (++as == P.ACC) { as = 0; pacc ^= 1; }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 4 + 4 * kEpiGroups) {
     // ============================================================ epilogue
-    const int q = warp - 4;  // TMEM lane quarter
-    for (int i = tid - 128; i < P.NT; i += 128) s_bias[i] = 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // kEpiGroups groups of four warps (one per TMEM lane quarter).  The 16-column chunks of a tile's accumulators are dealt
+    // round-robin to the groups, and a group requests its NEXT chunk from TMEM before it processes the current one, so the
+    // tcgen05.ld latency is hidden behind bias / pooling / stores (measured before: ~690 cycles per chunk, one group, no
+    // overlap = 22k cycles per 2-M-block tile that the single-buffered accumulator could not hide behind the MMAs).
+    const int q = (warp - 4) & 3;   // TMEM lane quarter
+    const int g = (warp - 4) >> 2;  // epilogue group
+    const int gt = tid - 128 - g * 128;  // thread index inside the group
+    const int bar_id = 1 + g;
+    float* bias_g = s_bias + g * 256;
+    float* xbuf_g = s_xbuf + g * (2 * 2 * 32 * 16);
+    auto gsync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
+    for (int i = gt; i < P.NT; i += 128) bias_g[i] = 0.f;
+    gsync();
     int as = 0, pacc = 0;
     int cur_pass = -1;
+    const int cpm = P.NT >> 4;            // chunks per M-block
+    const int nchunk = P.NMB * cpm;       // chunks per tile
     for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
       const int t = work / P.npass, pass = work - t * P.npass;
       int n, h0, w0;
       decode_tile(P, t, n, h0, w0);
       if (pass != cur_pass) {  // (re)load this pass's bias slice
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = tid - 128; i < P.NT; i += 128) s_bias[i] = P.bias[pass * P.NT + i];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        gsync();
+        for (int i = gt; i < P.NT; i += 128) bias_g[i] = P.bias[pass * P.NT + i];
+        gsync();
         cur_pass = pass;
       }
       ptx::mbar_wait(&acc_full[as], pacc);
@@ -225,74 +248,75 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
       const uint32_t acc_col = tmem_base + uint32_t(as * P.NMB * P.NT) + (uint32_t(q * 32) << 16);
       const int cbase = pass * P.NT;  // first output channel of this pass
       int xpar = 0;
-      for (int mb = 0; mb < P.NMB; ++mb) {
+      uint32_t raw[16];
+      int ci = g;
+      if (ci < nchunk) ptx::tmem_ld16(acc_col + uint32_t(ci << 4), raw);  // chunk ci sits at column ci*16 (mb*NT + c0)
+      for (; ci < nchunk; ci += kEpiGroups) {
+        const int mb = ci / cpm, c0 = (ci - mb * cpm) << 4;
         const int p = mb * 128 + q * 32 + lane;
         const int hh = p / P.WP, ww = p - hh * P.WP;
         const int h = h0 + hh, w = w0 + ww;
         const bool valid = hh < P.TH && ww < P.TW && h < P.H && w < P.W;
-        for (int c0 = 0; c0 < P.NT; c0 += 16) {
-          uint32_t raw[16];
-          ptx::tmem_ld16(acc_col + uint32_t(mb * P.NT + c0), raw);
-          ptx::tmem_wait_ld();
-          float v[16];
+        ptx::tmem_wait_ld();
+        float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float f = __uint_as_float(raw[j]) + s_bias[c0 + j];
-            if (P.relu) f = fmaxf(f, 0.f);
-            v[j] = f;
+        for (int j = 0; j < 16; ++j) {
+          float f = __uint_as_float(raw[j]) + bias_g[c0 + j];
+          if (P.relu) f = fmaxf(f, 0.f);
+          v[j] = f;
+        }
+        if (ci + kEpiGroups < nchunk) ptx::tmem_ld16(acc_col + uint32_t((ci + kEpiGroups) << 4), raw);
+        const int cg = cbase + c0;  // global output channel of v[0]
+        if (P.pool) {
+          // 2x2 max-pool: horizontal partner = lane^1, vertical partner = lane + WP inside this M-block
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+          const int rows_per_warp_shift = (P.WP == 64) ? 1 : 0;  // WP=64: warps (0,1)=row0,(2,3)=row1; WP=32: warp=row
+          const bool upper = rows_per_warp_shift ? (q >= 2) : (q & 1);
+          const int pair = rows_per_warp_shift ? (q & 1) : (q >> 1);
+          float* xb = xbuf_g + (xpar * 2 + pair) * (32 * 16);
+          if (upper) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xb[j * 32 + lane] = v[j];
           }
-          const int cg = cbase + c0;  // global output channel of v[0]
-          if (P.pool) {
-            // 2x2 max-pool: horizontal partner = lane^1, vertical partner = lane + WP inside this M-block
+          gsync();
+          if (!upper && valid && !(lane & 1) && cg < P.Cout) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-            const int rows_per_warp_shift = (P.WP == 64) ? 1 : 0;  // WP=64: warps (0,1)=row0,(2,3)=row1; WP=32: warp=row
-            const bool upper = rows_per_warp_shift ? (q >= 2) : (q & 1);
-            const int pair = rows_per_warp_shift ? (q & 1) : (q >> 1);
-            float* xb = s_xbuf + (xpar * 2 + pair) * (32 * 16);
-            if (upper) {
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], xb[j * 32 + lane]);
+            bf16* o = P.out + ((size_t(n) * (P.H >> 1) + (h >> 1)) * (P.W >> 1) + (w >> 1)) * P.out_ld + cg;
+            uint4 u0, u1;
+            u0.x = pack_bf16x2(v[0], v[1]); u0.y = pack_bf16x2(v[2], v[3]);
+            u0.z = pack_bf16x2(v[4], v[5]); u0.w = pack_bf16x2(v[6], v[7]);
+            u1.x = pack_bf16x2(v[8], v[9]); u1.y = pack_bf16x2(v[10], v[11]);
+            u1.z = pack_bf16x2(v[12], v[13]); u1.w = pack_bf16x2(v[14], v[15]);
+            *reinterpret_cast<uint4*>(o) = u0;
+            *reinterpret_cast<uint4*>(o + 8) = u1;
+          }
+          xpar ^= 1;
+        } else if (P.out_nchw) {
+          if (valid) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) xb[j * 32 + lane] = v[j];
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (!upper && valid && !(lane & 1) && cg < P.Cout) {
+            for (int j = 0; j < 16; ++j)
+              if (cg + j < P.Cout) {
+                float f = v[j];
+                if (P.sigmoid) f = 1.0f / (1.0f + __expf(-f));
+                P.out_nchw[((size_t(n) * P.Cout + cg + j) * P.H + h) * P.W + w] = f;
+              }
+          }
+        } else if (valid && cg < P.Cout) {
+          bf16* o = P.out + ((size_t(n) * P.H + h) * P.W + w) * P.out_ld + cg;
+          if (cg + 16 <= P.Cout) {
+            uint4 u0, u1;
+            u0.x = pack_bf16x2(v[0], v[1]); u0.y = pack_bf16x2(v[2], v[3]);
+            u0.z = pack_bf16x2(v[4], v[5]); u0.w = pack_bf16x2(v[6], v[7]);
+            u1.x = pack_bf16x2(v[8], v[9]); u1.y = pack_bf16x2(v[10], v[11]);
+            u1.z = pack_bf16x2(v[12], v[13]); u1.w = pack_bf16x2(v[14], v[15]);
+            *reinterpret_cast<uint4*>(o) = u0;
+            *reinterpret_cast<uint4*>(o + 8) = u1;
+          } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], xb[j * 32 + lane]);
-              bf16* o = P.out + ((size_t(n) * (P.H >> 1) + (h >> 1)) * (P.W >> 1) + (w >> 1)) * P.out_ld + cg;
-              uint4 u0, u1;
-              u0.x = pack_bf16x2(v[0], v[1]); u0.y = pack_bf16x2(v[2], v[3]);
-              u0.z = pack_bf16x2(v[4], v[5]); u0.w = pack_bf16x2(v[6], v[7]);
-              u1.x = pack_bf16x2(v[8], v[9]); u1.y = pack_bf16x2(v[10], v[11]);
-              u1.z = pack_bf16x2(v[12], v[13]); u1.w = pack_bf16x2(v[14], v[15]);
-              *reinterpret_cast<uint4*>(o) = u0;
-              *reinterpret_cast<uint4*>(o + 8) = u1;
-            }
-            xpar ^= 1;
-          } else if (P.out_nchw) {
-            if (valid) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (cg + j < P.Cout) {
-                  float f = v[j];
-                  if (P.sigmoid) f = 1.0f / (1.0f + __expf(-f));
-                  P.out_nchw[((size_t(n) * P.Cout + cg + j) * P.H + h) * P.W + w] = f;
-                }
-            }
-          } else if (valid && cg < P.Cout) {
-            bf16* o = P.out + ((size_t(n) * P.H + h) * P.W + w) * P.out_ld + cg;
-            if (cg + 16 <= P.Cout) {
-              uint4 u0, u1;
-              u0.x = pack_bf16x2(v[0], v[1]); u0.y = pack_bf16x2(v[2], v[3]);
-              u0.z = pack_bf16x2(v[4], v[5]); u0.w = pack_bf16x2(v[6], v[7]);
-              u1.x = pack_bf16x2(v[8], v[9]); u1.y = pack_bf16x2(v[10], v[11]);
-              u1.z = pack_bf16x2(v[12], v[13]); u1.w = pack_bf16x2(v[14], v[15]);
-              *reinterpret_cast<uint4*>(o) = u0;
-              *reinterpret_cast<uint4*>(o + 8) = u1;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (cg + j < P.Cout) o[j] = __float2bfloat16_rn(v[j]);
-            }
+            for (int j = 0; j < 16; ++j)
+              if (cg + j < P.Cout) o[j] = __float2bfloat16_rn(v[j]);
           }
         }
       }
@@ -302,7 +326,8 @@ __global__ void __launch_bounds__(512, 1) conv_umma_kernel(const __grid_constant
       if (++as == P.ACC) { as = 0; pacc ^= 1; }
     }
   } else if (warp >= 8) {
-    // ============================================================ A-tile builders (producer modes)
+    // ============================================================ A-tile builders (producer modes; in TMA mode warps 8-11 are
+    // the second epilogue group, handled above)
     if (IN_MODE != kInTma) {
       const int pw = warp - 8;
       int sa = 0, pa = 0;
@@ -446,7 +471,8 @@ bool choose_tiles(const ConvDesc& d, int NT, int in_mode, TileCfg* out) {
   const int nchunks = (d.Cin + 63) / 64;
   TileCfg best{};
   double best_cost = 1e300;
-  for (int NMB = 1; NMB * NT <= 512 && NMB <= 8; NMB *= 2) {
+  static const int nmb_max = getenv("CDAN_UMMA_NMB_MAX") ? atoi(getenv("CDAN_UMMA_NMB_MAX")) : 8;  // A/B switch
+  for (int NMB = 1; NMB * NT <= 512 && NMB <= nmb_max; NMB *= 2) {
     const int ACC = (2 * NMB * NT <= 512) ? 2 : 1;
     std::vector<int> wps;
     if (d.pool) {
@@ -467,21 +493,26 @@ bool choose_tiles(const ConvDesc& d, int NT, int in_mode, TileCfg* out) {
       const int a_stage = int(align_up(size_t(a_rows_alloc) * 128, 1024));
       const int tps = NT <= 32 ? taps : (NT == 64 ? std::min(taps, 3) : 1);
       const int b_stage = tps * NT * 128;
-      const int tail = 1024 + 256 * 4 + 2 * 2 * 32 * 16 * 4 + 64;
+      const int tail = 1024 + 2 * 256 * 4 + 2 * (2 * 2 * 32 * 16 * 4) + 64;
       // pipeline depth: as many stages as fit, capped
       int SA = (nchunks >= 2 || true) ? 2 : 1, SB = 4;
       auto total = [&](int sa, int sb) { return sa * a_stage + sb * b_stage + tail; };
       while (SB > 2 && total(SA, SB) > kSmemLimit) --SB;
       if (total(SA, SB) > kSmemLimit) continue;
       while (SA < 3 && total(SA + 1, SB) <= kSmemLimit && in_mode != kInTma) ++SA;
-      while (SB < kMaxSB && total(SA, SB + 1) <= kSmemLimit && SB < 6) ++SB;
+      static const int sb_max = getenv("CDAN_UMMA_SB_MAX") ? atoi(getenv("CDAN_UMMA_SB_MAX")) : 6;  // A/B switch
+      while (SB < kMaxSB && total(SA, SB + 1) <= kSmemLimit && SB < sb_max) ++SB;
       const double tiles = double((d.W + TW - 1) / TW) * ((d.H + TH - 1) / TH);
       // per-tile time model (cycles): tensor pipe vs L2->smem operand traffic, plus the epilogue when the
       // accumulator is single-buffered (then it cannot overlap the next tile's MMAs)
       const int ksteps_total = (d.Cin + 15) / 16;
       const double mma_cyc = double(NMB) * taps * ksteps_total * std::max(16.0, NT / 2.0);
       const double l2_bytes = double(nchunks) * (double(TH + 2 * halo) * WP * 128.0 + double(taps) * NT * 128.0);
-      const double epi_cyc = double(NMB) * (NT / 16.0) * 70.0 + 300.0;
+      // epilogue per 16-column chunk.  The fused 2x2 max-pool (shuffles + a shared-memory exchange and a group barrier per
+      // chunk) is expensive enough that it must overlap the next tile's MMAs: encoder.conv3 runs 2.28 ms with double-buffered
+      // accumulators (NMB = 1) against 2.67 ms with NMB = 2 (r02 A/B, CDAN_UMMA_NMB_MAX); the un-pooled layers measured the
+      // other way round (conv4 1.98 / 2.08, decoder.conv1 1.78 / 2.01 ms: halving the weight traffic into shared memory wins)
+      const double epi_cyc = double(NMB) * (NT / 16.0) * (d.pool ? 1200.0 : 70.0) + 300.0;
       const double cost = tiles * (std::max(mma_cyc, l2_bytes / 36.0) + (ACC == 1 ? epi_cyc : 0.15 * epi_cyc) + 200.0);
       if (cost < best_cost) {
         best_cost = cost;
@@ -611,7 +642,7 @@ int conv_umma_launch(const ConvDesc& d, const UmmaPack& pk, cudaStream_t stream)
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(P.ntiles * P.npass, sms);
-  const int threads = in_mode == kInTma ? 256 : 512;
+  const int threads = in_mode == kInTma ? 384 : 512;  // TMA mode: 4 role warps + two epilogue groups
   auto launch = [&](auto kern) -> int {
     CDAN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc.smem_bytes));
     kern<<<grid, threads, tc.smem_bytes, stream>>>(tmap, P);
