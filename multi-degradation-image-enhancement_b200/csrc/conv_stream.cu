@@ -1479,6 +1479,22 @@ int conv_stream_launch(const ConvDesc& d, const StreamPack& pk, cudaStream_t str
   P.TW = std::min(tw_max, kfold ? (ceil_div(d.W, P.strips) + 3) & ~3 : (ceil_div(d.W, P.strips) + 1) & ~1);
   const int want_segs = std::max(1, ceil_div(sms * 8, d.N * P.strips));
   P.SEG = std::max(std::min(32, d.H), (ceil_div(d.H, want_segs) + 1) & ~1);
+  // Small launches (a few images, or the 1/8-resolution layers of one image): with the 32-row floor most SMs get no item at
+  // all (one 1080p image at 1/8 resolution: 2 strips x 5 segments = 10 items for 148 SMs, 0.22 ms for a transition that takes
+  // 0.02 ms per image in a batch of 32).  Then pick the even height with the lowest cost = rounds of items per SM x (rows per
+  // item + re-read halo rows + pipeline fill); results do not depend on the segmentation (absolute-row ring slots).
+  if (long(d.N) * P.strips * ceil_div(d.H, P.SEG) < 2L * sms && d.H > 8) {
+    const int over = (fold == 3 ? 2 : 0) + 6;
+    long best = -1;
+    for (int seg = 8; seg <= ((d.H + 1) & ~1); seg += 2) {
+      const long items = long(d.N) * P.strips * ceil_div(d.H, seg);
+      const long cost = ((items + sms - 1) / sms) * (std::min(seg, d.H) + over);
+      if (best < 0 || cost <= best) {
+        best = cost;
+        P.SEG = seg;
+      }
+    }
+  }
   P.segs = ceil_div(d.H, P.SEG);
   P.nitems = d.N * P.strips * P.segs;
   P.relu = d.relu; P.sigmoid = d.sigmoid; P.Cout = d.Cout;
