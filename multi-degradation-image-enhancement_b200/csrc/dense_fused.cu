@@ -142,6 +142,30 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+// Loads of the parameter blob (weights, activation tables, group constants): written once before the roles start and never
+// again, so these need no ordering against the pipeline's barriers — NOT volatile, no memory clobber: the compiler may hoist
+// them out of the row loop or issue them early (the epilogue warps stall on shared-memory latency, ncu short_scoreboard 24 %).
+// Their addresses are derived from ordered_zero(), a volatile asm placed AFTER the wait for the blob copy: the loads depend on
+// its result, so they cannot be moved above that wait.
+__device__ __forceinline__ uint32_t ordered_zero() {
+  uint32_t z;
+  asm volatile("mov.u32 %0, 0;" : "=r"(z)::"memory");
+  return z;
+}
+__device__ __forceinline__ uint4 ldc128(uint32_t addr) {
+  uint4 v;
+  asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldc32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 ldc_f4(uint32_t addr) {
+  const uint4 u = ldc128(addr);
+  return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+}
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   const uint4 u = ptx::lds128(addr);
   return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
@@ -300,12 +324,14 @@ __device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, 
   const int NC = 3 - C;  // later layers that read it
   const int bar_id = 1 + C;
   const bool leader = q == C && lane == 0;  // the groups' leaders sit on different SM sub-partitions
+  ptx::mbar_wait_relaxed(S.w_full, 0);  // parameter blob resident
+  const uint32_t cz = ordered_zero();
   const uint32_t acc_free = S.acc_free + 32u * C, acc_done = S.acc_done + 32u * C;
   // consumer k of this layer's group: layer cp = C + 1 + k reads it through ring (cp, G); base slot and activation-table
   // address come from a small shared-memory table (one LDS with an immediate offset instead of a select chain per use)
-  const uint32_t gc = S.gconst + uint32_t(C) * 32u;
-  auto rbk = [&](int k) { return int(lds32(gc + 4u * k)); };
-  auto tabk = [&](int k) { return lds32(gc + 12u + 4u * k); };
+  const uint32_t gc = S.gconst + cz + uint32_t(C) * 32u;
+  auto rbk = [&](int k) { return int(ldc32(gc + 4u * k)); };
+  auto tabk = [&](int k) { return ldc32(gc + 12u + 4u * k); };
   Ring cr[3];
   Ring tsr;  // transition partial-sum ring position (rows [h0, h1) of every item, in order)
   uint32_t dpar = 0;  // acc_done phase parity per slot
@@ -313,11 +339,10 @@ __device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, 
   const bool idx_ok = idx >= G && idx < 128 - G;
   const uint32_t off0 = sw32_off(idx & 127, 0), off1 = sw32_off(idx & 127, 1);
   const uint32_t lb = S.tmem + (uint32_t(q * 32) << 16) + 96u * C;
-  const uint32_t tact_u = S.blob + kTActOff + uint32_t(G) * 32u;  // sc of this group's 16 channels (sh: + 160)
-  const uint32_t tw_u = S.blob + kTWOff + uint32_t(G) * 192u;     // [3 outputs][16 ch] fp32 of this group
+  const uint32_t tact_u = S.blob + cz + kTActOff + uint32_t(G) * 32u;  // sc of this group's 16 channels (sh: + 160)
+  const uint32_t tw_u = S.blob + cz + kTWOff + uint32_t(G) * 192u;     // [3 outputs][16 ch] fp32 of this group
   const uint32_t ts_in = S.ts_full + 8u * uint32_t(C * kTsDepth), ts_out = S.ts_full + 8u * uint32_t((C + 1) * kTsDepth);
   const uint32_t ts_addr0 = S.ts + uint32_t(idx & 127) * 16u;
-  ptx::mbar_wait_relaxed(S.w_full, 0);
   const size_t plane = size_t(P.H) * P.W;
   for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
     const Seg sg = decode_seg(P, item);
@@ -384,7 +409,7 @@ __device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, 
       //    the accumulator row (it is on the critical path of the chain)
       auto write_version = [&](int k) {
         const uint32_t tb = tabk(k);
-        const uint4 sc0 = ptx::lds128(tb), sc1 = ptx::lds128(tb + 16u), sh0 = ptx::lds128(tb + 32u), sh1 = ptx::lds128(tb + 48u);
+        const uint4 sc0 = ldc128(tb), sc1 = ldc128(tb + 16u), sh0 = ldc128(tb + 32u), sh1 = ldc128(tb + 48u);
         const __nv_bfloat162* c0p = reinterpret_cast<const __nv_bfloat162*>(&sc0);
         const __nv_bfloat162* c1p = reinterpret_cast<const __nv_bfloat162*>(&sc1);
         const __nv_bfloat162* h0p = reinterpret_cast<const __nv_bfloat162*>(&sh0);
@@ -426,7 +451,7 @@ __device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, 
       if (tsrow) {
         uint64_t av[8];
         {
-          const uint4 sc0 = ptx::lds128(tact_u), sc1 = ptx::lds128(tact_u + 16u), sh0 = ptx::lds128(tact_u + 160u), sh1 = ptx::lds128(tact_u + 176u);
+          const uint4 sc0 = ldc128(tact_u), sc1 = ldc128(tact_u + 16u), sh0 = ldc128(tact_u + 160u), sh1 = ldc128(tact_u + 176u);
           const __nv_bfloat162* c0p = reinterpret_cast<const __nv_bfloat162*>(&sc0);
           const __nv_bfloat162* c1p = reinterpret_cast<const __nv_bfloat162*>(&sc1);
           const __nv_bfloat162* h0p = reinterpret_cast<const __nv_bfloat162*>(&sh0);
@@ -445,7 +470,7 @@ __device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, 
           uint64_t acc = 0ull;
 #pragma unroll
           for (int h4 = 0; h4 < 4; ++h4) {
-            const uint4 w = ptx::lds128(tw_u + uint32_t(co) * 64u + uint32_t(h4) * 16u);
+            const uint4 w = ldc128(tw_u + uint32_t(co) * 64u + uint32_t(h4) * 16u);
             acc = ffma2((uint64_t(w.y) << 32) | w.x, av[2 * h4], acc);
             acc = ffma2((uint64_t(w.w) << 32) | w.z, av[2 * h4 + 1], acc);
           }
@@ -487,6 +512,7 @@ __device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, 
 __device__ __forceinline__ void loader(const FParams& P, const Smem& S, int t, int lane) {
   Ring gr, tsr;
   ptx::mbar_wait_relaxed(S.w_full, 0);
+  const uint32_t blob_c = S.blob + ordered_zero();  // base of the constant loads (ordered after the wait above)
   const uint32_t off0 = sw32_off(t, 0), off1 = sw32_off(t, 1);
   const int IH = P.H >> 1, IW = P.W >> 1;
   const size_t plane = size_t(P.H) * P.W;
@@ -548,7 +574,7 @@ __device__ __forceinline__ void loader(const FParams& P, const Smem& S, int t, i
         }
         group_sync(5);
         uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = make_uint4(0u, 0u, 0u, 0u);
-        float4 tsum = lds_f4(S.blob + kBiasOff + 4 * 64);  // transition bias
+        float4 tsum = ldc_f4(blob_c + kBiasOff + 4 * 64);  // transition bias
         if (col_ok) {
           const int r0 = dy ? 1 : 0, r1 = dy ? 2 : 1;
           const float wy0 = dy ? 0.75f : 0.25f, wy1 = dy ? 0.25f : 0.75f;
@@ -556,8 +582,8 @@ __device__ __forceinline__ void loader(const FParams& P, const Smem& S, int t, i
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) f[ch] = __float2bfloat16_rn((wy0 * hz[r0][ch] + wy1 * hz[r1][ch]) + xv[dy][ch]);
           // K slot k = 3*layer + channel (k = 12..15 unused: scale = shift = 0); tables stay in shared memory
-          const uint4 sc0 = ptx::lds128(S.blob + kG0TabOff), sh0 = ptx::lds128(S.blob + kG0TabOff + 32u);
-          const uint4 sc1 = ptx::lds128(S.blob + kG0TabOff + 16u), sh1 = ptx::lds128(S.blob + kG0TabOff + 48u);
+          const uint4 sc0 = ldc128(blob_c + kG0TabOff), sh0 = ldc128(blob_c + kG0TabOff + 32u);
+          const uint4 sc1 = ldc128(blob_c + kG0TabOff + 16u), sh1 = ldc128(blob_c + kG0TabOff + 48u);
           const __nv_bfloat162* c0p = reinterpret_cast<const __nv_bfloat162*>(&sc0);
           const __nv_bfloat162* h0p = reinterpret_cast<const __nv_bfloat162*>(&sh0);
           const __nv_bfloat162* c1p = reinterpret_cast<const __nv_bfloat162*>(&sc1);
@@ -583,7 +609,7 @@ __device__ __forceinline__ void loader(const FParams& P, const Smem& S, int t, i
             const __nv_bfloat162 a2 = __hfma2_relu(p2, *reinterpret_cast<const __nv_bfloat162*>(&tsc.y), *reinterpret_cast<const __nv_bfloat162*>(&tsh.y));
             const float av[3] = {__low2float(a01), __high2float(a01), __low2float(a2)};
 #pragma unroll
-            const float4 wa = lds_f4(S.blob + kTWOff), wb = lds_f4(S.blob + kTWOff + 64u), wc = lds_f4(S.blob + kTWOff + 128u);
+            const float4 wa = ldc_f4(blob_c + kTWOff), wb = ldc_f4(blob_c + kTWOff + 64u), wc = ldc_f4(blob_c + kTWOff + 128u);
             tsum.x = fmaf(wa.z, av[2], fmaf(wa.y, av[1], fmaf(wa.x, av[0], tsum.x)));
             tsum.y = fmaf(wb.z, av[2], fmaf(wb.y, av[1], fmaf(wb.x, av[0], tsum.y)));
             tsum.z = fmaf(wc.z, av[2], fmaf(wc.y, av[1], fmaf(wc.x, av[0], tsum.z)));

@@ -323,6 +323,70 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
 }
 
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2, clusters of two CTAs)
+// Two CTAs on the SMs of one TPC execute ONE tcgen05.mma of M = 256: CTA r supplies rows [128r, 128r+128) of A and rows
+// [N/2 r, N/2 (r+1)) of B from ITS shared memory (same offsets in both CTAs) and receives its 128 accumulator rows in ITS
+// tensor memory.  Only the leader (rank 0) issues MMAs and commits; every CTA streams half of the B operand, which halves
+// the shared-memory fill traffic per FLOP (the one-CTA kernel saturates the 128 B/clk shared-memory port: 12 KB of operand
+// reads + 4 KB of fills per 128-cycle N = 256 MMA).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // all threads of all CTAs of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address of this CTA) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {  // arrive on a barrier of any CTA of the cluster
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// shared::cluster address of the LEADER CTA's copy of a barrier, for the cta_group::2 TMA forms: in the shared::cluster window
+// of a CTA pair, bit 24 of an address selects the CTA; clearing it names the even (leader) CTA.
+__device__ __forceinline__ uint32_t leader_bar(const uint64_t* bar) { return smem_u32(bar) & 0xFEFFFFFFu; }
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {  // one warp (same warp id) in BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in BOTH CTAs once all MMAs issued so far have completed
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(uint16_t(3))
+               : "memory");
+}
+// tensor-map loads whose completion bytes are counted on the LEADER CTA's barrier
+__device__ __forceinline__ void tma2_load_4d(void* dst_smem, const void* tmap, int c0, int c1, int c2, int c3, const uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(leader_bar(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst_smem, const void* tmap, int c0, int c1, const uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+                   "r"(smem_u32(dst_smem)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(leader_bar(bar))
+               : "memory");
+}
+
 // ---------------------------------------------------------------- predicated single-thread instructions
 // Executed by every lane of a converged warp with warp-uniform operands; only the lane whose `leader` flag is set
 // performs the operation.  Keeping the control flow uniform lets ptxas hold descriptors / barrier addresses in uniform
