@@ -53,6 +53,9 @@ namespace {
 
 constexpr int kRowBytes = 4096;  // one operand row: 128 pixels x 16 channels bf16
 constexpr int kValidW = 120;     // output columns per strip
+#ifndef CDAN_FUSED_ONE_RELEASE
+#define CDAN_FUSED_ONE_RELEASE 1
+#endif
 #ifndef CDAN_FUSED_SLEEP_NS
 #define CDAN_FUSED_SLEEP_NS 32
 #endif
@@ -401,6 +404,7 @@ __device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, 
       }
       ptx::tmem_st16_zero(tm);
       if (shadow) ptx::tmem_st16_zero(ts);
+      if (C == 0 && leader) FTRACE(16, i);
       // 2. round to bf16 (the bias is folded into the consumers' activation shifts)
       __nv_bfloat162 raw[8];
 #pragma unroll
@@ -432,6 +436,11 @@ __device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, 
           ptx::sts128(base + off1, o1);
         }
       };
+#if CDAN_FUSED_ONE_RELEASE
+      // one release point per row (below): the chain of layers is throughput-bound, not latency-bound — the rings absorb the
+      // extra lag — and every release costs a proxy fence (drains the row's shared-memory stores) plus a group barrier
+      if (take[0]) write_version(0);
+#else
       if (take[0]) {
         write_version(0);
         ptx::fence_proxy_async_smem();
@@ -442,10 +451,12 @@ __device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, 
       if (leader) {
         arrive_a(acc_free + 8u * uint32_t(slot));
         if (take[0]) arrive_a(S.full + 8u * uint32_t(rbk(0) + cr[0].i));
-        FTRACE(13, i);
+        if (C == 0) FTRACE(13, i);
       }
+#endif
       if (take[1]) write_version(1);
       if (take[2]) write_version(2);
+      if (C == 0 && leader) FTRACE(14, i);
       // 4. this group's term of the 1x1 transition (16 channels x 3 outputs, packed fp32 FMAs) on top of the partial sums so
       //    far (loader: bias + F0 term; earlier layers in order)
       if (tsrow) {
@@ -490,6 +501,21 @@ __device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, 
       }
       if (C == 0 && leader) FTRACE(15, i);
       // 5. release the remaining versions and the partial sums
+#if CDAN_FUSED_ONE_RELEASE
+      {
+        ptx::fence_proxy_async_smem();
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before_sync();
+        group_sync(bar_id);
+        if (leader) {  // (dealing the waits / releases to lane 0 of all four warps measured slower: 8.08 vs 7.92 ms)
+          arrive_a(acc_free + 8u * uint32_t(slot));
+          if (take[0]) arrive_a(S.full + 8u * uint32_t(rbk(0) + cr[0].i));
+          if (take[1]) arrive_a(S.full + 8u * uint32_t(rbk(1) + cr[1].i));
+          if (take[2]) arrive_a(S.full + 8u * uint32_t(rbk(2) + cr[2].i));
+          if (tsrow) arrive_a(C < 3 ? ts_out + 8u * uint32_t(tsr.i) : S.ts_empty + 8u * uint32_t(tsr.i));
+        }
+      }
+#else
       if (take[1] || tsrow) {
         ptx::fence_proxy_async_smem();
         group_sync(bar_id);
@@ -499,6 +525,7 @@ __device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, 
           if (tsrow) arrive_a(C < 3 ? ts_out + 8u * uint32_t(tsr.i) : S.ts_empty + 8u * uint32_t(tsr.i));
         }
       }
+#endif
       if (leader) FTRACE(8 + C, i);
 #pragma unroll
       for (int k = 0; k < 3; ++k)
@@ -834,7 +861,7 @@ int fused_fd_launch(const FusedFdPack& pk, const void* t4, int t4_ld, const floa
     for (auto v : t) if (v && v < t0) t0 = v;
     fprintf(stderr, "FUSED TRACE N=%d H=%d W=%d SEG=%d segs=%d strips=%d items=%d\n", N, H, W, P.SEG, P.segs, P.strips, P.nitems);
     const char* names[kTraceRoles] = {"L0_issued", "L1_issued", "L2_issued", "L3_issued", "E0_start", "E1_start", "E2_start", "E3_start",
-                                      "E0_done", "E1_done", "E2_done", "E3_done", "loader", "E0_accfree", "E0_versions", "E0_tsterm", "E0_tsupd", "", "", ""};
+                                      "E0_done", "E1_done", "E2_done", "E3_done", "loader", "E0_accfree", "E0_versions", "E0_tsterm", "E0_drained", "", "", ""};
     for (int r = 0; r < 17; ++r) {
       fprintf(stderr, "%-10s", names[r]);
       for (int i = 0; i < kTraceRows; ++i) fprintf(stderr, " %7lld", t[r * kTraceRows + i] ? (long long)(t[r * kTraceRows + i] - t0) : -1ll);
