@@ -483,7 +483,10 @@ struct BandRun {
     m.top_send = size_t(dtop >> t.lvl) * row;
     m.bot_recv = size_t(h - (dbot >> t.lvl)) * row;
     m.bot_send = m.bot_recv - m.bytes;
-    CDAN_TRY(p->band_comm->exchange(m, s));
+    {
+      SpanGuard span(p, s, "band|halo_refresh");
+      CDAN_TRY(p->band_comm->exchange(m, s));
+    }
     const int nbrs = (p->band_comm->rank > 0) + (p->band_comm->rank + 1 < p->band_comm->nranks);
     p->band_stats.exchanges += 1;
     p->band_stats.halo_bytes_received += (long long)(m.bytes) * N * nbrs;
