@@ -507,7 +507,9 @@ __device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, 
         ptx::tmem_wait_st();
         ptx::tc_fence_before_sync();
         group_sync(bar_id);
-        if (leader) {  // (dealing the waits / releases to lane 0 of all four warps measured slower: 8.08 vs 7.92 ms)
+        // (measured slower: dealing the waits / releases to lane 0 of all four warps, 8.08 vs 7.92 ms; ONE group barrier per row
+        //  with the leader polling row i+1 before it releases row i, 9.57 ms — holding a row back costs the chain its slack)
+        if (leader) {
           arrive_a(acc_free + 8u * uint32_t(slot));
           if (take[0]) arrive_a(S.full + 8u * uint32_t(rbk(0) + cr[0].i));
           if (take[1]) arrive_a(S.full + 8u * uint32_t(rbk(1) + cr[1].i));
