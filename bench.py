@@ -50,9 +50,9 @@ DENSE3X3 = {f"{blk}.layers.{l}": (c0 + 16 * l, div)
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per 32 x 1080p step from the `ncu --set full` capture of ALL
 # launches of a step summarised in profiles/r02_step_ncu.md: the 12 dense-block 3x3 launches of dense blocks 1-3 (the final
 # dense block is one fused kernel), all 24 convolution launches, and the CBAM kernels.
-DENSE3X3_NCU_TRAFFIC_BYTES = 22317480000
-ALLCONV_NCU_TRAFFIC_BYTES = 50522824000
-CBAM_NCU_TRAFFIC_BYTES = 19543534000
+DENSE3X3_NCU_TRAFFIC_BYTES = 22317280000
+ALLCONV_NCU_TRAFFIC_BYTES = 50553688000
+CBAM_NCU_TRAFFIC_BYTES = 19545652000
 
 
 def measured_peaks():

@@ -75,21 +75,49 @@ __global__ void __launch_bounds__(256) gate_mlp_kernel(const float* __restrict__
                                                         int nblk, int C, int HW, const float* __restrict__ w1,
                                                         const float* __restrict__ b1, const float* __restrict__ w2,
                                                         const float* __restrict__ b2, float* __restrict__ gate) {
-  extern __shared__ float sm[];  // avg[C], mx[C], h_avg[R], h_max[R]
+  extern __shared__ float sm[];  // avg[C], mx[C], h_avg[R], h_max[R], red[2 * blockDim] (C < blockDim only)
   const int R = C / 16;
   float* avg = sm;
   float* mx = sm + C;
   float* ha = sm + 2 * C;
   float* hm = ha + R;
   const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  if (C < int(blockDim.x)) {
+    // fewer channels than threads (C = 64, 128): blockDim / C threads share a channel, each sums every parts-th partial
+    // (one 1080p image at 1/2 resolution has 270 partials per channel — a serial chain that long is most of this kernel's
+    // 20-60 us), then the parts are combined in a fixed order
+    float* red = hm + R;  // [parts][2][C]
+    const int parts = int(blockDim.x) / C, c = threadIdx.x % C, part = threadIdx.x / C;
     float ss = 0.f, mm = -INFINITY;
-    for (int b = 0; b < nblk; ++b) {
-      ss += psum[(size_t(n) * nblk + b) * C + c];
-      mm = fmaxf(mm, pmax[(size_t(n) * nblk + b) * C + c]);
+    if (part < parts)
+      for (int b = part; b < nblk; b += parts) {
+        ss += psum[(size_t(n) * nblk + b) * C + c];
+        mm = fmaxf(mm, pmax[(size_t(n) * nblk + b) * C + c]);
+      }
+    if (part < parts) {
+      red[(part * 2 + 0) * C + c] = ss;
+      red[(part * 2 + 1) * C + c] = mm;
     }
-    avg[c] = ss / float(HW);
-    mx[c] = mm;
+    __syncthreads();
+    if (threadIdx.x < C) {
+      float s2 = 0.f, m2 = -INFINITY;
+      for (int q = 0; q < parts; ++q) {
+        s2 += red[(q * 2 + 0) * C + threadIdx.x];
+        m2 = fmaxf(m2, red[(q * 2 + 1) * C + threadIdx.x]);
+      }
+      avg[threadIdx.x] = s2 / float(HW);
+      mx[threadIdx.x] = m2;
+    }
+  } else {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float ss = 0.f, mm = -INFINITY;
+      for (int b = 0; b < nblk; ++b) {
+        ss += psum[(size_t(n) * nblk + b) * C + c];
+        mm = fmaxf(mm, pmax[(size_t(n) * nblk + b) * C + c]);
+      }
+      avg[c] = ss / float(HW);
+      mx[c] = mm;
+    }
   }
   __syncthreads();
   // hidden layer: one warp per hidden unit (round-robin), lanes stride over C
@@ -308,7 +336,7 @@ int cbam_typed(const void* x, int x_ld, const void* mul, int mul_ld, void* out, 
     pool_finish_kernel<<<N, 256, 0, s>>>(sc.psum, sc.pmax, nblk, C, N, sc.pooled);
     CDAN_CUDA_OK(cudaGetLastError());
     CDAN_TRY(band->comm->allreduce_sum_max(sc.pooled, sc.pooled + size_t(N) * C, N * C, s));
-    gate_mlp_kernel<<<N, 256, (2 * C + 2 * (C / 16)) * sizeof(float), s>>>(sc.pooled, sc.pooled + size_t(N) * C, 1, C, band->HW_full,
+    gate_mlp_kernel<<<N, 256, (2 * C + 2 * (C / 16) + 512) * sizeof(float), s>>>(sc.pooled, sc.pooled + size_t(N) * C, 1, C, band->HW_full,
                                                                            wt.w1, wt.b1, wt.w2, wt.b2, sc.gate);
     CDAN_CUDA_OK(cudaGetLastError());
   } else {
@@ -317,7 +345,7 @@ int cbam_typed(const void* x, int x_ld, const void* mul, int mul_ld, void* out, 
                                                                                       sc.psum, sc.pmax, size_t(HW));
       CDAN_CUDA_OK(cudaGetLastError());
     }
-    gate_mlp_kernel<<<N, 256, (2 * C + 2 * (C / 16)) * sizeof(float), s>>>(sc.psum, sc.pmax, sc.nblk, C, HW, wt.w1, wt.b1,
+    gate_mlp_kernel<<<N, 256, (2 * C + 2 * (C / 16) + 512) * sizeof(float), s>>>(sc.psum, sc.pmax, sc.nblk, C, HW, wt.w1, wt.b1,
                                                                            wt.w2, wt.b2, sc.gate);
     CDAN_CUDA_OK(cudaGetLastError());
   }
