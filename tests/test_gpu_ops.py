@@ -53,6 +53,13 @@ CONV_CASES = [
     (1, 64, 3, 40, 140, 3, False, True, False),    # decoder.conv4
     (1, 64, 128, 36, 250, 3, False, True, True),   # encoder.conv2, several tiles
     (1, 128, 64, 33, 150, 3, False, True, False),  # decoder.conv3
+    # CTA-pair tile kernel (cta_group::2): odd tile counts (the last pair computes one tile twice, copy masked), fused pool,
+    # two N-passes, two M-blocks per weight stage
+    (1, 128, 256, 20, 36, 3, False, True, True),   # encoder.conv3 class: pooled epilogue, 5 x 2 = 10 tiles
+    (3, 128, 256, 12, 30, 3, False, True, True),   # 3 images x 3 tiles = 9 tiles (odd)
+    (1, 256, 512, 19, 70, 3, False, True, False),  # encoder.conv4 class, two 256-channel passes
+    (3, 256, 128, 9, 50, 3, False, True, False),   # decoder.conv2 class (NT = 128: 64 + 64 rows per CTA)
+    (1, 512, 256, 13, 31, 3, False, True, False),  # decoder.conv1 class, one ragged tile row
 ]
 
 
