@@ -136,7 +136,25 @@ __device__ __forceinline__ void epilogue_role(const KParams& P, int warp, int la
       }
       if (ci + kEpiGroups < nchunk) ptx::tmem_ld16(acc_col + uint32_t((ci + kEpiGroups) << 4), raw);
       const int cg = cbase + c0;  // global output channel of v[0]
-      if (P.pool) {
+      if (P.pool && P.WP == 16) {
+        // 2x2 max-pool with 16-pixel tile rows: a warp holds two image rows, so both partners are lanes of the same warp
+        // (lane^1 and lane^16) — no shared-memory exchange and no group barrier per chunk
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+          v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 16));
+        }
+        if (valid && !(lane & 17) && cg < P.Cout) {
+          bf16* o = P.out + ((size_t(n) * (P.H >> 1) + (h >> 1)) * (P.W >> 1) + (w >> 1)) * P.out_ld + cg;
+          uint4 u0, u1;
+          u0.x = pack_bf16x2(v[0], v[1]); u0.y = pack_bf16x2(v[2], v[3]);
+          u0.z = pack_bf16x2(v[4], v[5]); u0.w = pack_bf16x2(v[6], v[7]);
+          u1.x = pack_bf16x2(v[8], v[9]); u1.y = pack_bf16x2(v[10], v[11]);
+          u1.z = pack_bf16x2(v[12], v[13]); u1.w = pack_bf16x2(v[14], v[15]);
+          *reinterpret_cast<uint4*>(o) = u0;
+          *reinterpret_cast<uint4*>(o + 8) = u1;
+        }
+      } else if (P.pool) {
         // 2x2 max-pool: horizontal partner = lane^1, vertical partner = lane + WP inside this M-block
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
@@ -660,7 +678,12 @@ bool choose_tiles(const ConvDesc& d, int NT, int in_mode, TileCfg* out, bool pai
     const int ACC = (2 * NMB * NT <= 512) ? 2 : 1;
     std::vector<int> wps;
     if (d.pool) {
-      wps = {32, 64};
+      // 16-pixel tile rows keep both pooling partners inside a warp (epilogue_role: no shared-memory exchange, no group
+      // barrier), but only 14 of 16 columns are outputs: measured slower for encoder.conv3 (2.26 vs 2.05 ms with 32-pixel
+      // rows) — the pooled epilogue is not what limits the pair kernel.  Kept behind the A/B switch CDAN_UMMA_POOL_WP=16.
+      static const int pool_wp = getenv("CDAN_UMMA_POOL_WP") ? atoi(getenv("CDAN_UMMA_POOL_WP")) : 0;
+      if (pool_wp == 16 || pool_wp == 32 || pool_wp == 64) wps = {pool_wp};
+      else wps = {32, 64};
     } else {
       for (int wp = 2 * halo + 2; wp <= std::min(256, d.W + 2 * halo + 6); wp += 2) wps.push_back(wp);
       if (d.W + 2 * halo <= 256) wps.push_back(d.W + 2 * halo);
@@ -696,7 +719,7 @@ bool choose_tiles(const ConvDesc& d, int NT, int in_mode, TileCfg* out, bool pai
       // chunk) is expensive enough that it must overlap the next tile's MMAs: encoder.conv3 runs 2.28 ms with double-buffered
       // accumulators (NMB = 1) against 2.67 ms with NMB = 2 (r02 A/B, CDAN_UMMA_NMB_MAX); the un-pooled layers measured the
       // other way round (conv4 1.98 / 2.08, decoder.conv1 1.78 / 2.01 ms: halving the weight traffic into shared memory wins)
-      const double epi_cyc = double(NMB) * (NT / 16.0) * (d.pool ? 1200.0 : 70.0) + 300.0;
+      const double epi_cyc = double(NMB) * (NT / 16.0) * (d.pool ? (WP == 16 ? 500.0 : 1200.0) : 70.0) + 300.0;
       // operand bytes per cycle and SM the fills sustain next to the MMA's own operand reads; CTA pairs measured a little
       // better with two M-blocks per weight stage on the un-pooled layers (conv4 1.79 / 1.85 ms), hence the lower rate there
       const double fill_rate = pair ? 30.0 : 36.0;
