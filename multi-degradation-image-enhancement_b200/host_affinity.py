@@ -37,11 +37,45 @@ def gpu_numa_node(device_index: int) -> Optional[int]:
         return None
 
 
+def gpu_cpu_affinity_from_topo(device_index: int):
+    """Fallback when sysfs carries no NUMA node for the GPU's PCI function (containers often show -1): the CPU-affinity column
+    of `nvidia-smi topo -m`.  Returns (cpu set, numa node or None) or (None, None)."""
+    import re
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+    except Exception:
+        return None, None
+    for line in out.splitlines():
+        fields = [f.strip() for f in re.split(r"\t+|\s{2,}", line.strip()) if f.strip()]
+        if not fields or fields[0] != f"GPU{device_index}":
+            continue
+        for k, f in enumerate(fields[1:], start=1):
+            if re.fullmatch(r"\d+(-\d+)?(,\d+(-\d+)?)*", f) and ("-" in f or "," in f):
+                node = int(fields[k + 1]) if k + 1 < len(fields) and fields[k + 1].isdigit() else None
+                return _parse_cpulist(f), node
+    return None, None
+
+
 def bind_to_gpu_node(device_index: int) -> Dict[str, object]:
     """Restrict this process to the CPUs of the GPU's NUMA node.  Returns a small report for the bench JSON line."""
     node = gpu_numa_node(device_index)
     report: Dict[str, object] = {"gpu": device_index, "numa_node": node, "bound": False}
     if node is None:
+        cpus, node = gpu_cpu_affinity_from_topo(device_index)
+        report["numa_node"] = node
+        if cpus:
+            try:
+                target = cpus & os.sched_getaffinity(0)
+                if target and len(target) < len(os.sched_getaffinity(0)):
+                    os.sched_setaffinity(0, target)
+                    report["bound"] = True
+                    report["cpus"] = len(target)
+                    report["source"] = "nvidia-smi topo -m"
+                else:
+                    report["note"] = "GPU affinity covers all allowed CPUs (single NUMA node visible)"
+            except Exception as exc:  # pragma: no cover - depends on the host
+                report["error"] = str(exc)
         return report
     try:
         with open(f"/sys/devices/system/node/node{node}/cpulist") as f:

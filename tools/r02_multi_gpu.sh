@@ -4,6 +4,7 @@
 set -u
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+nvidia-smi topo -m > gpurun_out/r02m_topo.txt 2>&1; lscpu | grep -i "numa\|model name\|^CPU(s)" >> gpurun_out/r02m_topo.txt
 timeout 300 python -m pytest tests/test_gpu_band.py -x -q -k nccl 2>&1 | tail -2
 python bench.py --config c5 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02m_c5_n1.json 2> gpurun_out/r02m_c5_n1.err
 for n in 2 4 8; do
