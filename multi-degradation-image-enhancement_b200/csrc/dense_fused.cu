@@ -53,6 +53,9 @@ namespace {
 
 constexpr int kRowBytes = 4096;  // one operand row: 128 pixels x 16 channels bf16
 constexpr int kValidW = 120;     // output columns per strip
+#ifndef CDAN_FUSED_GCONST_LDS
+#define CDAN_FUSED_GCONST_LDS 1  // 0: ring constants by select chains instead of a shared-memory table — measured 10.4 vs 7.9 ms (register spills)
+#endif
 #ifndef CDAN_FUSED_ONE_RELEASE
 #define CDAN_FUSED_ONE_RELEASE 1
 #endif
@@ -333,8 +336,18 @@ __device__ __forceinline__ void epilogue_layer(const FParams& P, const Smem& S, 
   // consumer k of this layer's group: layer cp = C + 1 + k reads it through ring (cp, G); base slot and activation-table
   // address come from a small shared-memory table (one LDS with an immediate offset instead of a select chain per use)
   const uint32_t gc = S.gconst + cz + uint32_t(C) * 32u;
+#if CDAN_FUSED_GCONST_LDS
   auto rbk = [&](int k) { return int(ldc32(gc + 4u * k)); };
   auto tabk = [&](int k) { return ldc32(gc + 12u + 4u * k); };
+#else
+  // closed forms of ring_base_fast(C+1+k, C+1) and of the table address of ring_id(C+1+k, C+1): two selects instead of a
+  // shared-memory load at the head of every version's dependent chain (k is a compile-time constant at every use)
+  (void)gc;
+  auto rbk = [&](int k) { return kG0Depth + (k == 0 ? (C == 0 ? 0 : (C == 1 ? 8 : 23)) : (k == 1 ? (C == 0 ? 3 : 18) : 11)); };
+  auto tabk = [&](int k) {
+    return S.blob + cz + kTabOff + 64u * uint32_t(k == 0 ? (C == 0 ? 0 : (C == 1 ? 2 : 5)) : (k == 1 ? (C == 0 ? 1 : 4) : 3));
+  };
+#endif
   Ring cr[3];
   Ring tsr;  // transition partial-sum ring position (rows [h0, h1) of every item, in order)
   uint32_t dpar = 0;  // acc_done phase parity per slot
