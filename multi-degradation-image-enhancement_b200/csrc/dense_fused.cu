@@ -850,7 +850,8 @@ int fused_fd_launch(const FusedFdPack& pk, const void* t4, int t4_ld, const floa
     const int seg = (ceil_div(H, segs) + 1) & ~1;
     const int nseg = ceil_div(H, seg);
     const long items = long(N) * P.strips * nseg;
-    const long cost = ((items + sms - 1) / sms) * (seg + 18);
+    static const int seg_over = getenv("CDAN_FUSED_SEG_OVERHEAD") ? atoi(getenv("CDAN_FUSED_SEG_OVERHEAD")) : 18;  // A/B switch
+    const long cost = ((items + sms - 1) / sms) * (seg + seg_over);
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
       P.SEG = seg;
