@@ -50,7 +50,10 @@ CDAN_API int cdan_plan_destroy(cdan_plan* plan);
 CDAN_API int cdan_plan_load_weights(cdan_plan* plan, int n, const char* const* keys, const void* const* ptrs,
                            const int64_t* numels);
 
-/* Options: "host_chunk" = images per step of the host-buffer copy/compute pipeline (default 0 = auto: 16 x 1080p of pixels);
+/* Options: "host_chunk" = largest sub-batch of the host-buffer copy/compute pipeline (default 0 = auto: 16 x 1080p of pixels; the
+ *                        schedule ramps up to it and down again, see cdan_forward_host);
+ *          "fd_fused"  = 1 (default) final dense block as one fused kernel on bf16 plans, 0 = layer by layer (also materialises
+ *                        the "dec.final_in" stage tap);
  *          "conv_impl" = 0 auto (tcgen05 where supported), 1 force CUDA-core path;
  *          "profile"   = 1 brackets every launch group with CUDA events on the launching stream. */
 CDAN_API int cdan_plan_set_option(cdan_plan* plan, const char* name, int value);
@@ -61,9 +64,10 @@ CDAN_API int cdan_workspace_bytes(cdan_plan* plan, int N, int H, int W, size_t* 
 /* CDAN.forward in eval mode (reference models/cdan.py:171-176).  x, y: fp32 NCHW contiguous [N,3,H,W] on the plan's
  * device.  H % 8 != 0 or W % 8 != 0 is an error (the reference fails with a size mismatch there too). */
 CDAN_API int cdan_forward(cdan_plan* plan, void* stream, const float* x, float* y, int N, int H, int W);
-/* Same through HOST buffers (pinned memory recommended): the batch is processed in sub-batches of "host_chunk" images;
- * the H2D copy of the next and the D2H copy of the previous sub-batch overlap the forward of the current one on
- * separate streams.  Returns after the last D2H copy has completed. */
+/* Same through HOST buffers (pinned memory recommended): the batch is processed in sub-batches — a geometric ramp from about one
+ * 1080p image of pixels up to "host_chunk" images and down again, so that the first H2D and the last D2H copy are short and every
+ * other copy hides behind a neighbouring forward; the H2D copy of the next and the D2H copy of the previous sub-batch overlap the
+ * forward of the current one on separate streams.  Results do not depend on the schedule.  Returns after the last D2H copy. */
 CDAN_API int cdan_forward_host(cdan_plan* plan, const float* x_host, float* y_host, int N, int H, int W);
 /* The reference's real data path end to end (uint8 image -> /255 -> forward -> x255 -> uint8; data/dataset.py:86-92 with
  * `A.Normalize(0,1,255)` + `ToTensorV2`, models/model.py:80-83): x_host, y_host are interleaved uint8 [N,H,W,3] HOST buffers.
